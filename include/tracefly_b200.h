@@ -1,0 +1,244 @@
+/* tracefly_b200.h — C-ABI of the B200-native TraceFly GA hot path.
+ *
+ * One shared library (libtracefly_b200.so, sm_100a only, no CPU fallback) whose
+ * entry points are what a binding for the reference's GA path would call.  All
+ * signatures are plain C: pointers, sizes, PODs.  No torch / C++ types.
+ *
+ * Reference files (under the upstream repo root):
+ *   HR  = UAV_Navigation/path_planning_GA/path_planner_hrmaga.py
+ *   PF  = UAV_Navigation/path_planning_GA/GA_complex _PF.py
+ *   GAE = uav-backend/app/routers/GA_enhanced.py
+ *
+ * Conventions
+ *   - every `*_dev` pointer is CALLER-OWNED device memory (e.g. a torch tensor's
+ *     data_ptr()), valid until `stream` reaches the operation; the library never
+ *     allocates per call (scratch is sized by tf_*_workspace_bytes and passed in).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     every call is asynchronous on that stream.
+ *   - return value: TF_OK (0) or a negative tf_status; never throws, never exits.
+ *   - population layout: f32[P][W][4] (x, y, z, pad) — one waypoint = one float4 —
+ *     or, for the reference-order f64 entry points, f64[P][W][4].
+ *   - lens_dev: i32[P] valid waypoint count per chromosome (<= W), or NULL = all W.
+ *   - collision flags: u32[P][ceil(W/32)], bit i of word k = waypoint 32k+i collides.
+ */
+#ifndef TRACEFLY_B200_H
+#define TRACEFLY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TF_VERSION 100 /* 0.1.0 */
+
+typedef enum tf_status {
+    TF_OK = 0,
+    TF_ERR_INVALID = -1,     /* NULL pointer / bad enum / bad flag            */
+    TF_ERR_SHAPE = -2,       /* P, W, N, k out of the supported range         */
+    TF_ERR_UNSUPPORTED = -3, /* combination not built                          */
+    TF_ERR_CUDA = -4,        /* a CUDA runtime call failed (see tf_last_cuda_error) */
+    TF_ERR_NOMEM = -5,
+    TF_ERR_NODEVICE = -6,    /* no sm_100 device: there is no fallback path    */
+    TF_ERR_WORKSPACE = -7    /* workspace too small                            */
+} tf_status;
+
+#define TF_W_MAX 256   /* waypoints per chromosome supported by the warp-per-chromosome kernels */
+#define TF_TOPK_MAX 8192
+
+/* ---- environment ---------------------------------------------------------------- */
+
+/* Obstacle semantics: which reference collision / distance rules apply. */
+typedef enum tf_semantics {
+    TF_SEM_NONE = 0,
+    TF_SEM_HR = 1, /* HR:17-28  sphere test ||p-c|| <= size + safety_radius; nearest distance to CENTRES */
+    TF_SEM_PF = 2  /* PF:28-59  cube / sphere / cylinder(=AABB s,s,2s) collision; distances per PF:46-59 */
+} tf_semantics;
+
+typedef enum tf_kind {
+    TF_KIND_SPHERE = 0,   /* PF:37-39, PF:54-55 */
+    TF_KIND_CUBE = 1,     /* PF:34-36 collision = Chebyshev <= size; PF:52-53 distance is spherical */
+    TF_KIND_CYLINDER = 2, /* PF:40-42 collision = AABB (s,s,2s); PF:56-57 distance = max(0,|dz|-2s) */
+    TF_KIND_AABB = 3      /* extension: half extents (hx,hy,hz), true box distance */
+} tf_kind;
+
+/* 32-byte host record; `size` < 0 means "absent" -> HR default 1.0 (HR:20). */
+typedef struct tf_obstacle {
+    float cx, cy, cz, size;
+    float hx, hy, hz; /* TF_KIND_AABB only */
+    int32_t kind;     /* tf_kind; ignored under TF_SEM_HR */
+} tf_obstacle;
+
+/* Moving sphere (extension, BASELINE configs[3]): c(t) = c0 + v * t, t = waypoint index;
+ * HR rules (radius = size + safety_radius, distance to centre). */
+typedef struct tf_dyn_obstacle {
+    float cx, cy, cz, size;
+    float vx, vy, vz, _pad;
+} tf_dyn_obstacle;
+
+typedef struct tf_env tf_env; /* opaque; owns its device copy of the obstacle tables */
+
+/* obs_host: n records on the HOST (copied; kind-sorted and pre-squared on the way in). */
+int tf_env_create(int semantics, const tf_obstacle* obs_host, int n, float safety_radius, tf_env** out);
+int tf_env_set_dynamic(tf_env* env, const tf_dyn_obstacle* dyn_host, int n, float safety_radius);
+/* Bit-packed occupancy grid in BRICK layout (see tf_voxel_*): caller-owned device memory,
+ * must stay alive while the env uses it.  nx, ny, nz multiples of 8.  NULL detaches. */
+int tf_env_set_voxels(tf_env* env, const uint32_t* bricks_dev, int nx, int ny, int nz);
+/* Hazard heat-map f32[nt][ny][nx] (caller-owned device memory).  A waypoint i at (x, y)
+ * samples tri-linearly at gx = x*sx + ox, gy = y*sy + oy, gt = i*st (clamped).  NULL detaches. */
+int tf_env_set_hazard(tf_env* env, const float* hazard_dev, int nt, int ny, int nx,
+                      float sx, float sy, float ox, float oy, float st);
+int tf_env_destroy(tf_env* env);
+
+/* Brick layout: the grid is tiled in 8x8x8-voxel bricks of 16 u32 (64 B); brick index =
+ * bx + (nx/8) * (by + (ny/8) * bz); inside a brick word = (z&7)*2 + ((y&7)>>2),
+ * bit = ((y&3)<<3) | (x&7).  One 32-B sector therefore covers 8x8x4 voxels. */
+int64_t tf_voxel_grid_bytes(int nx, int ny, int nz);
+/* Rasterise analytic obstacles (PF collision rules; HR if semantics == TF_SEM_HR with
+ * radius size + safety_radius) into a zeroed brick grid: voxel (x,y,z) is set iff the
+ * lattice point (x,y,z) collides.  obs_dev: tf_obstacle[n] on the DEVICE. */
+int tf_voxelize(int semantics, const tf_obstacle* obs_dev, int n, float safety_radius,
+                uint32_t* bricks_dev, int nx, int ny, int nz, void* stream);
+/* Linear bit grid (bit index x + nx*(y + ny*z), LSB first in u32 words) -> brick layout. */
+int tf_voxel_pack_linear(const uint32_t* linear_dev, uint32_t* bricks_dev, int nx, int ny, int nz, void* stream);
+
+/* ---- fitness (replaces Path.calculate_fitness HR:42-59 / PF:144-170) -------------- */
+
+typedef struct tf_params {
+    float w_safety, w_energy, w_wind, w_time, w_turn; /* HR:55-59: 0.4 0.2 0.2 0.1 0.1 */
+    int32_t dist_zero_guard;    /* 1: time_score = 0 when distance == 0 (HR:53); 0: 1/0 = inf (PF:163) */
+    float hazard_weight;        /* extension: wind = 1/(1 + alt + hazard_weight * sum hazard) ; 0 = off */
+    int32_t samples_per_segment; /* extension: S >= 1 collision/proximity samples per segment; 1 = reference */
+} tf_params;
+
+void tf_params_default(tf_params* p);
+
+/* FP32 throughput kernel, one warp per chromosome, fixed reduction order.
+ * fit_dev f32[P]; coll_dev u32[P][ceil(W/32)] or NULL. */
+int tf_fitness(const tf_env* env, const float* pop_dev, const int32_t* lens_dev, int P, int W,
+               const tf_params* params, float* fit_dev, uint32_t* coll_dev, void* stream);
+
+/* FP64 reference-order kernel: the reference's exact operation order (sequential sums,
+ * sqrt(dot) norms), so that on identical inputs fitness is BIT-IDENTICAL to HR/PF in
+ * float64 and the stable ranking cannot diverge.  pop64_dev f64[P][W][4]; fit64_dev f64[P]. */
+int tf_fitness_f64(const tf_env* env, const double* pop64_dev, const int32_t* lens_dev, int P, int W,
+                   const tf_params* params, double* fit64_dev, uint32_t* coll_dev, void* stream);
+
+/* ---- ranking (replaces population.sort(key=fitness, reverse=True) HR:114 / PF:193) -- */
+
+/* Stable descending top-k: order = (fitness desc, index asc); `worst` != 0 returns instead
+ * the k LAST entries of that order, worst first.  k <= TF_TOPK_MAX.  idx_dev i32[k]. */
+int64_t tf_topk_workspace_bytes(int P, int k, int f64);
+int tf_rank_topk(const float* fit_dev, int P, int k, int worst, int32_t* idx_dev,
+                 void* workspace_dev, int64_t workspace_bytes, void* stream);
+int tf_rank_topk_f64(const double* fit64_dev, int P, int k, int worst, int32_t* idx_dev,
+                     void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* ---- selection + crossover + mutation (HR:85-99,114-122; PF:192-208) --------------- */
+
+typedef enum tf_selection {
+    TF_SEL_TRUNCATION = 0, /* HR:118: 2 distinct uniform picks from the sorted top n_top */
+    TF_SEL_TOURNAMENT = 1  /* extension: best of tournament_k uniform entrants, per parent */
+} tf_selection;
+typedef enum tf_crossover {
+    TF_CX_SINGLE_POINT = 0, /* HR:85-89: cp in [1, min(L1,L2)-2]; c1 = p1[:cp]+p2[cp:], c2 = p2[:cp]+p1[cp:] */
+    TF_CX_UNIFORM = 1       /* extension: interior waypoints swapped by an iid bit mask */
+} tf_crossover;
+typedef enum tf_mutation {
+    TF_MUT_LATTICE = 0,     /* HR:91-99: with prob rate, one interior waypoint += d, d in {-1,0,1}^3 */
+    TF_MUT_LATTICE_PF = 1,  /* PF:202-208: any waypoint (endpoints included) += d, d in {-1,+1}^3 */
+    TF_MUT_GAUSSIAN = 2     /* extension: one interior waypoint += sigma * z, z ~ N(0,1)^3 (Irwin-Hall 8) */
+} tf_mutation;
+
+typedef struct tf_ga_params {
+    int32_t n_elite;       /* HR:115: 2 — first n_elite of the ranking are copied to slots 0.. */
+    int32_t selection;     /* tf_selection */
+    int32_t n_top;         /* truncation pool size (HR:118: 10) */
+    int32_t tournament_k;  /* 1..32 */
+    int32_t crossover;     /* tf_crossover */
+    int32_t mutation;      /* tf_mutation */
+    float mutation_rate;   /* HR:62: 0.1 */
+    float sigma;           /* TF_MUT_GAUSSIAN */
+    uint32_t stream_id;    /* Philox counter word 2: island / rank id */
+    int32_t _pad;
+} tf_ga_params;
+
+void tf_ga_params_default(tf_ga_params* p);
+
+/* Draw tape: host-supplied random draws, one 32-byte record per CHILD PAIR j (children
+ * land in slots n_elite+2j, n_elite+2j+1; a slot >= P is dropped, HR:122).
+ *   pa, pb : positions in the ranking (truncation) or population indices (tournament)
+ *   cp     : crossover point
+ *   mp1/2  : mutated waypoint of child 1/2, or -1 = gate failed (rand() >= rate)
+ *   d1/d2  : packed delta, 2 bits per axis: (dx+1) | (dy+1)<<2 | (dz+1)<<4
+ * This is exactly the information HR:118-120 draws from np.random, in that order. */
+typedef struct tf_draw {
+    int32_t pa, pb, cp, mp1, d1, mp2, d2, _pad;
+} tf_draw;
+
+/* One GA step: next_pop <- elites + children.  tape_dev == NULL -> counter-based
+ * Philox4x32-10 keyed by `seed`, counter (pair, generation, stream_id, call).
+ * top_idx_dev: i32[max(n_elite, n_top)] from tf_rank_topk.  Optional parity outputs:
+ * sel_dev i32[npairs][2] (population indices of both parents), cp_dev i32[npairs]. */
+int tf_ga_step(const float* pop_dev, const int32_t* lens_dev, const float* fit_dev,
+               const int32_t* top_idx_dev, const tf_draw* tape_dev, uint64_t seed, uint32_t generation,
+               const tf_ga_params* ga, int P, int W, float* next_pop_dev, int32_t* next_lens_dev,
+               int32_t* sel_dev, int32_t* cp_dev, void* stream);
+int tf_ga_step_f64(const double* pop64_dev, const int32_t* lens_dev, const double* fit64_dev,
+                   const int32_t* top_idx_dev, const tf_draw* tape_dev, uint64_t seed, uint32_t generation,
+                   const tf_ga_params* ga, int P, int W, double* next_pop64_dev, int32_t* next_lens_dev,
+                   int32_t* sel_dev, int32_t* cp_dev, void* stream);
+
+/* Fused generation (FP32, fixed W): builds each child in registers, writes it to
+ * next_pop and evaluates its fitness in the same warp — the child is never re-read.
+ * Results are identical to tf_ga_step followed by tf_fitness. */
+int tf_generation(const tf_env* env, const float* pop_dev, const float* fit_dev,
+                  const int32_t* top_idx_dev, const tf_draw* tape_dev, uint64_t seed, uint32_t generation,
+                  const tf_ga_params* ga, const tf_params* params, int P, int W,
+                  float* next_pop_dev, float* next_fit_dev, uint32_t* next_coll_dev,
+                  int32_t* sel_dev, int32_t* cp_dev, void* stream);
+
+/* HR:126-128 best tracking: if fit[slot] > *best_fit then { *best_fit = fit[slot];
+ * best_path <- pop[slot]; *best_gen = generation }. */
+int tf_track_best(const float* pop_dev, const float* fit_dev, int slot, int W, uint32_t generation,
+                  float* best_fit_dev, float* best_path_dev, int32_t* best_gen_dev, void* stream);
+int tf_track_best_f64(const double* pop64_dev, const double* fit64_dev, int slot, int W, uint32_t generation,
+                      double* best_fit_dev, double* best_path_dev, int32_t* best_gen_dev, void* stream);
+
+/* ---- initial populations --------------------------------------------- */
+
+/* HR:68-80 diagonal lattice walk start -> end, replicated P times (HR:82-83).  Returns the
+ * walk length through *w_out when pop_dev == NULL (sizing call, host only). */
+int tf_init_diagonal(const double start[3], const double end[3], int P, int W, float* pop_dev,
+                     int* w_out, void* stream);
+/* Seeded +-1 lattice random walks (Philox) from per-chromosome or common start, clipped to
+ * [lo, hi] per axis: the synthetic populations of BASELINE configs[1..4]. */
+int tf_init_walks(uint64_t seed, const float* start_dev /* f32[P][4] or NULL */, const float start[3],
+                  const float lo[3], const float hi[3], int P, int W, float* pop_dev, void* stream);
+
+/* ---- island migration (either side of the NCCL all-gather) --------------- */
+
+/* rows_dev f32[E][W][4], rfit_dev f32[E] <- pop[elite_idx[e]], fit[elite_idx[e]]. */
+int tf_pack_elites(const float* pop_dev, const float* fit_dev, const int32_t* elite_idx_dev, int E, int W,
+                   float* rows_dev, float* rfit_dev, void* stream);
+/* gathered rows f32[world][E][W][4] / fit f32[world][E]; the j-th FOREIGN elite (source rank
+ * ascending, skipping self_rank, then elite rank) overwrites pop[worst_idx[j]], fit[...]. */
+int tf_replace_worst(float* pop_dev, float* fit_dev, const int32_t* worst_idx_dev, int W,
+                     const float* gathered_rows_dev, const float* gathered_fit_dev,
+                     int world, int self_rank, int E, void* stream);
+
+/* ---- misc ------------------------------------------------------------------------------ */
+int tf_version(void);
+const char* tf_strerror(int status);
+int tf_last_cuda_error(void);               /* cudaError_t of the last failing runtime call on this thread */
+int tf_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes);
+/* Philox4x32-10 block, exposed so host code and tests can reproduce device draws. */
+void tf_philox4x32_10(uint32_t key0, uint32_t key1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                      uint32_t out[4]);
+/* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
+int64_t tf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRACEFLY_B200_H */

@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Generate the golden input/output vectors under tests/golden/ by running the
+UNMODIFIED TraceFly reference (imported read-only from /root/reference).
+
+The reference has no tests and no golden vectors of its own, and
+being Python it cannot travel to the GPU box, so the vectors made here are the
+pin for oracle/ and, through it, for the CUDA path.
+
+    python -B tests/golden/gen_golden.py            # writes tests/golden/*.npz
+
+Recorded with CPython 3.12.3 / NumPy 2.3.5 (versions are stored in each file).
+Every array is produced by reference code: HR = path_planner_hrmaga.py,
+PF = "GA_complex _PF.py".  Nothing in this script restates the algorithm; it
+only builds inputs, calls the reference and records what it returned (plus the
+np.random draws it consumed, via wrappers, i.e. the "draw tape").
+"""
+import json
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_loader  # noqa: E402
+
+META = {"numpy": np.__version__, "python": sys.version.split()[0],
+        "generator": "tests/golden/gen_golden.py"}
+
+
+# --------------------------------------------------------------------------- inputs
+def lattice_walks(rng, P, W, start, lo, hi):
+    """Seeded +-1 lattice random walks (what HR:91-99 mutation produces)."""
+    steps = rng.integers(-1, 2, size=(P, W - 1, 3))
+    wp = np.concatenate([np.zeros((P, 1, 3), np.int64), np.cumsum(steps, axis=1)], axis=1)
+    wp = wp + np.asarray(start, np.int64)
+    return np.clip(wp, lo, hi)
+
+
+def as_tuples(row, n, to_py):
+    """Waypoint tuples typed the way the reference's own generators type them (HR:68-80,
+    PF:95-119): the first waypoint is the caller's tuple of Python scalars, every later one
+    is a tuple of NumPy scalars (np.int64 / np.float64).  This matters: CPython >= 3.12
+    sum() switches to compensated summation for runs of exact Python floats, which pure
+    Python-scalar paths could trigger; NumPy-scalar paths sum naively, left to right."""
+    np_t = np.int64 if to_py is int else np.float64
+    return [tuple((to_py if i == 0 else np_t)(v) for v in row[i]) for i in range(n)]
+
+
+def hr_obstacles(pos, size):
+    out = []
+    for p, s in zip(pos, size):
+        d = {"position": [float(v) if isinstance(v, (float, np.floating)) else int(v) for v in p]}
+        if s is not None and not (isinstance(s, float) and np.isnan(s)):
+            d["size"] = s
+        out.append(d)
+    return out
+
+
+# --------------------------------------------------------------------------- HR fitness
+def gen_fitness_hr(hr):
+    rng = np.random.default_rng(1234)
+    cases = []
+
+    def run_case(name, wp, lens, pos, size, to_py):
+        P, W, _ = wp.shape
+        obstacles = hr_obstacles(pos, size)
+        fit = np.zeros(P)
+        coll = np.zeros((P, W), bool)
+        dnear = np.full((P, W), np.inf)
+        for p in range(P):
+            path = hr.Path(as_tuples(wp[p], lens[p], to_py))
+            path.calculate_fitness(obstacles)
+            fit[p] = path.fitness
+            for i, pt in enumerate(path.waypoints):
+                coll[p, i] = hr.is_collision(pt, obstacles)
+                dnear[p, i] = hr.distance_to_nearest_obstacle(pt, obstacles)
+        cases.append(name)
+        sz = np.array([np.nan if s is None else float(s) for s in size], np.float64)
+        return {f"{name}/wp": wp.astype(np.float64), f"{name}/lens": lens.astype(np.int32),
+                f"{name}/obs_pos": np.asarray(pos, np.float64).reshape(-1, 3),
+                f"{name}/obs_size": sz, f"{name}/fitness": fit, f"{name}/collide": coll,
+                f"{name}/dnear": dnear}
+
+    out = {}
+    # lattice chromosomes, integer obstacles with integer sizes (PF:17-26 distribution)
+    for (P, W, N) in [(64, 3, 4), (128, 16, 10), (128, 20, 10), (96, 32, 64), (48, 64, 32), (32, 33, 7)]:
+        wp = lattice_walks(rng, P, W, (10, 10, 5), 0, 24)
+        pos = rng.integers(0, 24, size=(N, 3))
+        size = [int(s) for s in rng.integers(1, 5, size=N)]
+        out.update(run_case(f"lat_W{W}_N{N}", wp, np.full(P, W), pos, size, int))
+    # producer never writes "size" (lidar_hybrid_model_validate.py:150-154) -> default 1.0 (HR:20)
+    wp = lattice_walks(rng, 64, 16, (8, 8, 4), 0, 16)
+    pos = rng.integers(0, 16, size=(12, 3))
+    out.update(run_case("lat_nosize", wp, np.full(64, 16), pos, [None] * 12, int))
+    # N = 0 -> distance inf -> proximity term 0 (HR:26-27)
+    out.update(run_case("lat_noobs", wp[:16], np.full(16, 16), np.zeros((0, 3)), [], int))
+    # boundary: points exactly at ||p-c|| == size + 2 (Pythagorean offsets), and one step outside
+    c = np.array([10, 10, 10])
+    offs = np.array([[3, 0, 0], [0, 3, 0], [1, 2, 2], [2, 1, 2], [2, 2, 1], [0, 0, 3],
+                     [4, 0, 0], [3, 1, 0], [2, 2, 2], [1, 1, 3], [0, 0, 0], [6, 0, 0],
+                     [4, 4, 2], [3, 4, 0], [0, 5, 0], [5, 1, 0]])
+    wp = (c + offs)[None, :, :].repeat(2, axis=0)
+    wp[1] = wp[1][::-1]
+    out.update(run_case("boundary_r3", wp, np.full(2, 16), c[None, :], [1], int))
+    out.update(run_case("boundary_r6", wp, np.full(2, 16), c[None, :], [4], int))
+    # all waypoints identical -> distance == 0 guard (HR:53), turns == 0
+    wp = np.tile(np.array([[[3, 3, 3]]]), (4, 8, 1))
+    out.update(run_case("zero_dist", wp, np.full(4, 8), rng.integers(0, 8, size=(3, 3)), [1, 2, 3], int))
+    # float (non-lattice) waypoints as MAIN:52-56 produces, float obstacle positions/sizes
+    wpf = lattice_walks(rng, 64, 12, (5, 5, 5), 0, 12).astype(np.float64)
+    wpf += rng.uniform(-0.45, 0.45, size=wpf.shape)
+    posf = rng.uniform(0, 12, size=(9, 3))
+    sizef = [float(s) for s in rng.uniform(0.5, 3.0, size=9)]
+    out.update(run_case("float_W12_N9", wpf, np.full(64, 12), posf, sizef, float))
+    # ragged lengths inside one batch
+    wp = lattice_walks(rng, 40, 24, (10, 10, 5), 0, 24)
+    lens = rng.integers(3, 25, size=40)
+    pos = rng.integers(0, 24, size=(10, 3))
+    size = [int(s) for s in rng.integers(1, 5, size=10)]
+    out.update(run_case("ragged_W24", wp, lens, pos, size, int))
+    out["meta"] = np.array(json.dumps(dict(META, cases=cases, ref="HR:17-28,33-59")))
+    np.savez_compressed(os.path.join(HERE, "fitness_hr.npz"), **out)
+    print("fitness_hr.npz:", len(cases), "cases")
+
+
+# --------------------------------------------------------------------------- PF fitness
+KINDS = ["sphere", "cube", "cylinder"]
+
+
+class _Env:
+    pass
+
+
+def gen_fitness_pf(pf):
+    rng = np.random.default_rng(4321)
+    cases = []
+    out = {}
+
+    def run_case(name, wp, lens, pos, size, kind, to_py):
+        P, W, _ = wp.shape
+        env = pf.ComplexEnvironment.__new__(pf.ComplexEnvironment)
+        env.obstacles = [{"shape": KINDS[k], "position": tuple(to_py(v) for v in p), "size": to_py(s)}
+                         for p, s, k in zip(pos, size, kind)]
+        fit = np.zeros(P)
+        coll = np.zeros((P, W), bool)
+        dnear = np.full((P, W), np.inf)
+        with np.errstate(divide="ignore"):
+            for p in range(P):
+                path = pf.Path(as_tuples(wp[p], lens[p], to_py))
+                path.calculate_fitness(env)
+                fit[p] = path.fitness
+                for i, pt in enumerate(path.waypoints):
+                    coll[p, i] = env.is_obstacle(pt)
+                    dnear[p, i] = env.distance_to_obstacles(pt)
+        cases.append(name)
+        out.update({f"{name}/wp": wp.astype(np.float64), f"{name}/lens": lens.astype(np.int32),
+                    f"{name}/obs_pos": np.asarray(pos, np.float64).reshape(-1, 3),
+                    f"{name}/obs_size": np.asarray(size, np.float64),
+                    f"{name}/obs_kind": np.asarray(kind, np.int32),
+                    f"{name}/fitness": fit, f"{name}/collide": coll, f"{name}/dnear": dnear})
+
+    for (P, W, N) in [(64, 3, 6), (128, 16, 10), (128, 21, 10), (96, 32, 96), (48, 64, 33)]:
+        wp = lattice_walks(rng, P, W, (10, 10, 5), 0, 24)
+        pos = rng.integers(0, 24, size=(N, 3))
+        size = rng.integers(1, 5, size=N)
+        kind = rng.integers(0, 3, size=N)
+        run_case(f"lat_W{W}_N{N}", wp, np.full(P, W), pos, size, kind, int)
+    # one kind only (exercises empty kind buckets)
+    for k in range(3):
+        wp = lattice_walks(rng, 32, 16, (8, 8, 4), 0, 16)
+        pos = rng.integers(0, 16, size=(8, 3))
+        size = rng.integers(1, 5, size=8)
+        run_case(f"only_{KINDS[k]}", wp, np.full(32, 16), pos, size, np.full(8, k), int)
+    run_case("noobs", wp[:8], np.full(8, 16), np.zeros((0, 3)), [], [], int)
+    # boundary offsets around one obstacle of each kind with size 3
+    c = np.array([10, 10, 10])
+    offs = np.array([[3, 0, 0], [3, 3, 3], [1, 2, 2], [2, 2, 1], [3, 3, 6], [3, 3, 7], [0, 0, 6],
+                     [4, 0, 0], [3, 1, 0], [2, 2, 2], [0, 0, 0], [3, 4, 0], [0, 0, 7], [4, 3, 6],
+                     [1, 1, 3], [2, 1, 2]])
+    wp = (c + offs)[None].repeat(2, axis=0)
+    wp[1] = wp[1][::-1]
+    for k in range(3):
+        run_case(f"boundary_{KINDS[k]}", wp, np.full(2, 16), c[None], [3], [k], int)
+    # float inputs
+    wpf = lattice_walks(rng, 64, 12, (5, 5, 5), 0, 12).astype(np.float64)
+    wpf += rng.uniform(-0.45, 0.45, size=wpf.shape)
+    posf = rng.uniform(0, 12, size=(9, 3))
+    sizef = rng.uniform(0.5, 3.0, size=9)
+    run_case("float_W12_N9", wpf, np.full(64, 12), posf, sizef, rng.integers(0, 3, size=9), float)
+    # ragged (PF populations have mixed lengths)
+    wp = lattice_walks(rng, 40, 24, (10, 10, 5), 0, 24)
+    lens = rng.integers(3, 25, size=40)
+    pos = rng.integers(0, 24, size=(10, 3))
+    run_case("ragged_W24", wp, lens, pos, rng.integers(1, 5, size=10), rng.integers(0, 3, size=10), int)
+    # all-identical waypoints: PF has no distance guard (PF:163) -> numpy 1/0.0 = inf
+    wp = np.tile(np.array([[[3, 3, 3]]]), (2, 6, 1))
+    run_case("zero_dist", wp, np.full(2, 6), rng.integers(0, 8, size=(3, 3)), [1, 2, 3], [0, 1, 2], int)
+    out["meta"] = np.array(json.dumps(dict(META, cases=cases, kinds=KINDS, ref="PF:28-59,141-170")))
+    np.savez_compressed(os.path.join(HERE, "fitness_pf.npz"), **out)
+    print("fitness_pf.npz:", len(cases), "cases")
+
+
+# --------------------------------------------------------------------------- HR evolve traces
+class Recorder:
+    """Wraps np.random.{choice,randint,rand} to record the draws the reference
+    consumes, in order, without changing what they return."""
+
+    def __init__(self):
+        self.events = []
+        self._orig = {}
+
+    def __enter__(self):
+        for name in ("choice", "randint", "rand"):
+            self._orig[name] = getattr(np.random, name)
+            setattr(np.random, name, self._wrap(name, self._orig[name]))
+        return self
+
+    def __exit__(self, *exc):
+        for name, fn in self._orig.items():
+            setattr(np.random, name, fn)
+
+    def _wrap(self, name, fn):
+        def inner(*a, **k):
+            r = fn(*a, **k)
+            self.events.append((name, a, k, r))
+            return r
+        return inner
+
+
+def pack_delta(d):
+    return int((d[0] + 1) | ((d[1] + 1) << 2) | ((d[2] + 1) << 4))
+
+
+def gen_evolve_hr(hr, pf, name, P, rate, G, start, end, obstacles, seed):
+    sweeps = []  # one list per calculate_fitness call: (waypoints, fitness)
+    orig_cf = hr.Path.calculate_fitness
+
+    def cf(self, obs):
+        orig_cf(self, obs)
+        sweeps.append((np.array(self.waypoints, dtype=np.float64), float(self.fitness)))
+
+    hr.Path.calculate_fitness = cf
+    np.random.seed(seed)
+    t0 = time.time()
+    try:
+        with Recorder() as rec:
+            ga = hr.HRMAGAGenerator(P, rate, G)
+            best = ga.evolve(start, end, obstacles)
+    finally:
+        hr.Path.calculate_fitness = orig_cf
+    dt = time.time() - t0
+    W = len(best)
+    assert len(sweeps) == (G + 1) * P
+    pops = np.stack([s[0] for s in sweeps]).reshape(G + 1, P, W, 3)
+    fits = np.array([s[1] for s in sweeps]).reshape(G + 1, P)
+    # decode the event stream into the canonical per-pair tape (see include/tracefly_b200.h)
+    npairs = (P - 2 + 1) // 2
+    tape = np.zeros((G, npairs, 8), np.int32)
+    gates = np.zeros((G, npairs, 2), np.float64)
+    ev = iter(rec.events)
+    for g in range(G):
+        for j in range(npairs):
+            nm, a, k, r = next(ev)
+            assert nm == "choice" and len(a[0]) == min(10, P)
+            pool = a[0]
+            ia = [i for i, x in enumerate(pool) if x is r[0]][0]
+            ib = [i for i, x in enumerate(pool) if x is r[1]][0]
+            nm, a, k, cp = next(ev)
+            assert nm == "randint"
+            row = [ia, ib, int(cp)]
+            for c in range(2):
+                nm, a, k, gate = next(ev)
+                assert nm == "rand"
+                gates[g, j, c] = gate
+                if gate < rate:
+                    nm, a, k, mp = next(ev)
+                    assert nm == "randint"
+                    nm, a, k, d = next(ev)
+                    assert nm == "choice" and len(d) == 3
+                    row += [int(mp), pack_delta(d)]
+                else:
+                    row += [-1, 0]
+            tape[g, j, :7] = row
+    assert next(ev, None) is None
+    opos = np.array([o["position"] for o in obstacles], np.float64).reshape(-1, 3)
+    osz = np.array([o.get("size", np.nan) for o in obstacles], np.float64)
+    units = (G + 1) * P * (W - 1)
+    meta = dict(META, P=P, rate=rate, G=G, start=list(start), end=list(end), seed=seed, W=W,
+                ref="HR:101-130", ref_seconds=dt, units=units, units_per_s=units / dt)
+    np.savez_compressed(os.path.join(HERE, f"evolve_hr_{name}.npz"),
+                        pops=pops.astype(np.int16 if np.all(pops == np.round(pops)) else np.float64),
+                        fits=fits, tape=tape, gates=gates, best=np.array(best, np.float64),
+                        obs_pos=opos, obs_size=osz, meta=np.array(json.dumps(meta)))
+    print(f"evolve_hr_{name}.npz: {dt:.1f}s reference wall, W={W}, {units / dt:.0f} units/s")
+
+
+def pf_seeded_obstacles(pf, seed, bounds, n):
+    """PF:17-26 obstacle generator driven at a fixed seed (PF:256-259 scenario)."""
+    random.seed(seed)
+    np.random.seed(seed)
+    env = pf.ComplexEnvironment(*bounds, n)
+    return env
+
+
+def gen_evolve_pf(pf):
+    """PF:255-267 default scenario at seed 0: records the (never-changing)
+    population, the per-generation fitness and best_path()."""
+    env = pf_seeded_obstacles(pf, 0, ((0, 20), (0, 20), (0, 10)), 10)
+    t0 = time.time()
+    ga = pf.GeneticAlgorithm(population_size=50, mutation_rate=0.1, generations=100, environment=env,
+                             source=(0, 0, 0), destination=(15, 15, 8))
+    init = [list(p.waypoints) for p in ga.population]
+    ga.evolve()
+    dt = time.time() - t0
+    final = [list(p.waypoints) for p in ga.population]
+    P = len(final)
+    Wmax = max(len(p) for p in final)
+    wp = np.zeros((P, Wmax, 3))
+    lens = np.zeros(P, np.int32)
+    for i, p in enumerate(final):
+        lens[i] = len(p)
+        wp[i, :len(p)] = np.array(p, np.float64)
+    fit = np.array([p.fitness for p in ga.population])
+    best = np.array(ga.best_path().waypoints, np.float64)
+    units = 100 * int(np.sum(lens - 1))
+    meta = dict(META, ref="PF:255-269", seed=0, ref_seconds=dt, units=units, units_per_s=units / dt,
+                same_as_init=bool(sorted(map(str, init)) == sorted(map(str, final))))
+    np.savez_compressed(os.path.join(HERE, "evolve_pf_default.npz"), wp=wp, lens=lens, fitness=fit, best=best,
+                        obs_pos=np.array([o["position"] for o in env.obstacles], np.float64),
+                        obs_size=np.array([o["size"] for o in env.obstacles], np.float64),
+                        obs_kind=np.array([KINDS.index(o["shape"]) for o in env.obstacles], np.int32),
+                        meta=np.array(json.dumps(meta)))
+    print(f"evolve_pf_default.npz: {dt:.1f}s reference wall, lens {sorted(set(lens.tolist()))}")
+
+
+def main():
+    hr = ref_loader.load_hr()
+    pf = ref_loader.load_pf()
+    which = set(sys.argv[1:]) or {"fitness", "evolve"}
+    if "fitness" in which:
+        gen_fitness_hr(hr)
+        gen_fitness_pf(pf)
+    if "evolve" in which:
+        rng = np.random.default_rng(7)
+        obs_small = hr_obstacles(rng.integers(0, 16, size=(10, 3)), [int(s) for s in rng.integers(1, 5, size=10)])
+        # the reference's own defaults (HR:62): pop 50, mut 0.1, gens 100; SURVEY §6 scenario
+        gen_evolve_hr(hr, pf, "default", 50, 0.1, 100, (0, 0, 0), (15, 15, 8), obs_small, seed=0)
+        # high mutation rate, odd population (exercises the truncated last pair, HR:122)
+        gen_evolve_hr(hr, pf, "odd_hot", 21, 0.9, 40, (2, 1, 0), (9, 12, 4), obs_small, seed=3)
+        # P < 10 -> top pool is the whole population (HR:118)
+        gen_evolve_hr(hr, pf, "tiny", 6, 0.5, 30, (0, 0, 0), (6, 3, 2), obs_small[:3], seed=5)
+        # BASELINE configs[0] / SURVEY §8d cfg 1: pop 100, 20 waypoints, 200 generations
+        env = pf_seeded_obstacles(pf, 0, ((0, 20), (0, 20), (0, 10)), 10)
+        obs_cfg1 = [{"position": [int(v) for v in o["position"]], "size": int(o["size"])} for o in env.obstacles]
+        gen_evolve_hr(hr, pf, "cfg1", 100, 0.1, 200, (0, 0, 0), (19, 19, 8), obs_cfg1, seed=0)
+        gen_evolve_pf(pf)
+
+
+if __name__ == "__main__":
+    main()
