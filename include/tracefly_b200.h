@@ -80,6 +80,9 @@ typedef struct tf_env tf_env; /* opaque; owns its device copy of the obstacle ta
 
 /* obs_host: n records on the HOST (copied; kind-sorted and pre-squared on the way in). */
 int tf_env_create(int semantics, const tf_obstacle* obs_host, int n, float safety_radius, tf_env** out);
+/* Same, from float64 records (n x 8 doubles: cx cy cz size hx hy hz kind).  The FP64
+ * reference-order kernels then see positions / sizes / safety radius unrounded. */
+int tf_env_create_f64(int semantics, const double* obs64_host, int n, double safety_radius, tf_env** out);
 int tf_env_set_dynamic(tf_env* env, const tf_dyn_obstacle* dyn_host, int n, float safety_radius);
 /* Bit-packed occupancy grid in BRICK layout (see tf_voxel_*): caller-owned device memory,
  * must stay alive while the env uses it.  nx, ny, nz multiples of 8.  NULL detaches. */
@@ -123,6 +126,13 @@ int tf_fitness(const tf_env* env, const float* pop_dev, const int32_t* lens_dev,
  * float64 and the stable ranking cannot diverge.  pop64_dev f64[P][W][4]; fit64_dev f64[P]. */
 int tf_fitness_f64(const tf_env* env, const double* pop64_dev, const int32_t* lens_dev, int P, int W,
                    const tf_params* params, double* fit64_dev, uint32_t* coll_dev, void* stream);
+
+/* Point queries in the reference's float64 arithmetic: is_collision (HR:17-23) /
+ * distance_to_nearest_obstacle (HR:25-28) / ComplexEnvironment.is_obstacle (PF:28-44) /
+ * distance_to_obstacles (PF:46-59) for n points.  pts64_dev f64[n][4]; collide_dev i32[n] or
+ * NULL; dnear_dev f64[n] or NULL (inf when the environment has no obstacles). */
+int tf_point_query_f64(const tf_env* env, const double* pts64_dev, int n, int32_t* collide_dev,
+                       double* dnear_dev, void* stream);
 
 /* ---- ranking (replaces population.sort(key=fitness, reverse=True) HR:114 / PF:193) -- */
 
@@ -211,6 +221,8 @@ int tf_track_best_f64(const double* pop64_dev, const double* fit64_dev, int slot
  * walk length through *w_out when pop_dev == NULL (sizing call, host only). */
 int tf_init_diagonal(const double start[3], const double end[3], int P, int W, float* pop_dev,
                      int* w_out, void* stream);
+int tf_init_diagonal_f64(const double start[3], const double end[3], int P, int W, double* pop64_dev,
+                         int* w_out, void* stream);
 /* Seeded +-1 lattice random walks (Philox) from per-chromosome or common start, clipped to
  * [lo, hi] per axis: the synthetic populations of BASELINE configs[1..4]. */
 int tf_init_walks(uint64_t seed, const float* start_dev /* f32[P][4] or NULL */, const float start[3],

@@ -53,3 +53,29 @@ def rel_err(a, ref):
 def tape_from_golden(tape_g):
     """[npairs, 8] int32 golden tape rows are already in tf_draw layout."""
     return np.ascontiguousarray(tape_g, np.int32)
+
+
+# ----------------------------------------------------------------------------- GPU-side helpers
+def gpu_env_from_table(B, L, sem, table64, safety=2.0):
+    return B.Environment(sem, table64, safety)
+
+
+def random_table(rng, N, world, sem_pf=True, max_size=4, aabb=False):
+    t = np.zeros((N, 8))
+    t[:, :3] = rng.integers(0, world, size=(N, 3))
+    t[:, 3] = rng.integers(1, max_size + 1, size=N)
+    if sem_pf:
+        t[:, 7] = rng.integers(0, 4 if aabb else 3, size=N)
+        t[:, 4:7] = rng.integers(1, max_size + 1, size=(N, 3))
+    return t
+
+
+def oracle_env_from_table(sem, table64, safety=2.0, **kw):
+    kind = table64[:, 7].astype(np.int32)
+    obs32 = O.obstacle_table(table64[:, :3], table64[:, 3], kind, half=table64[:, 4:7])
+    obs64 = table64.copy()
+    return O.OracleEnv(sem, obs32, safety, **kw).with_obs64(obs64)
+
+
+def as_u32(t):
+    return t.cpu().numpy().view(np.uint32)

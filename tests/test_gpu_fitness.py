@@ -1,0 +1,173 @@
+"""GPU parity: tf_fitness / tf_fitness_f64 / tf_point_query_f64 through the C-ABI (ctypes) vs
+  (1) goldens recorded from the unmodified reference, and (2) the CPU oracle on seeded inputs.
+Bars: collision flags bit-exact; FP32 fitness bit-exact vs the fixed-order oracle and within
+1e-5 relative of the reference (north_star); FP64 fitness bit-identical to the reference."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as O
+from tests.helpers import (as_u32, golden_case, load_golden, oracle_env_from_table, random_table, rel_err,
+                           unpack_bits, valid_mask)
+
+pytestmark = pytest.mark.gpu
+FIT_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def tf():
+    import torch
+    from tracefly_b200 import _lib as L
+    from tracefly_b200 import batched as B
+    assert torch.cuda.is_available()
+    return torch, L, B
+
+
+def _cases(fam):
+    return load_golden(f"fitness_{fam}.npz")[1]["cases"]
+
+
+@pytest.mark.parametrize("fam,case", [("hr", c) for c in _cases("hr")] + [("pf", c) for c in _cases("pf")])
+def test_golden_cases(tf, fam, case):
+    torch, L, B = tf
+    g, _ = load_golden(f"fitness_{fam}.npz")
+    d = golden_case(g, fam, case)
+    sem = L.SEM_HR if fam == "hr" else L.SEM_PF
+    env = B.Environment(sem, d["obs64"], 2.0)
+    P, W, _ = d["pop64"].shape
+    valid = valid_mask(d["lens"], W)
+    lens = torch.from_numpy(d["lens"]).cuda()
+    prm = L.default_params(dist_zero_guard=1 if fam == "hr" else 0)
+
+    # float64 reference-order kernel: bit-identical to the reference
+    pop64 = torch.from_numpy(d["pop64"]).cuda()
+    f64, c64 = B.fitness_batch_f64(pop64, lens, env, prm)
+    assert np.array_equal(f64.cpu().numpy(), d["fitness"])
+    assert np.array_equal(unpack_bits(as_u32(c64), W) & valid, d["collide"] & valid)
+
+    # FP32 throughput kernel: flags bit-exact, fitness bit-exact vs oracle and 1e-5 vs reference
+    pop32 = pop64.float()
+    f32, c32 = B.fitness_batch(pop32, lens, env, prm)
+    assert np.array_equal(unpack_bits(as_u32(c32), W) & valid, d["collide"] & valid)
+    assert rel_err(f32.cpu().numpy(), d["fitness"]) <= FIT_RTOL
+    oenv = O.OracleEnv(O.SEM_HR if fam == "hr" else O.SEM_PF, d["obs32"], 2.0)
+    of32, oc32 = O.fitness_f32(oenv, d["pop64"].astype(np.float32), d["lens"], O.default_params(guard=prm.dist_zero_guard))
+    assert np.array_equal(of32, f32.cpu().numpy())
+    assert np.array_equal(oc32, as_u32(c32))
+
+    # point queries (is_collision / distance_to_nearest_obstacle, is_obstacle / distance_to_obstacles)
+    pts = d["pop64"][:, :, :3].reshape(-1, 3)
+    coll, dn = B.point_query_f64(pts, env)
+    vm = valid.reshape(-1)
+    assert np.array_equal(coll[vm], d["collide"].reshape(-1)[vm])
+    assert np.array_equal(dn[vm], d["dnear"].reshape(-1)[vm])
+
+
+@pytest.mark.parametrize("sem", ["hr", "pf"])
+@pytest.mark.parametrize("P,W,N", [(1, 3, 1), (777, 20, 10), (4096, 32, 1024), (1500, 64, 257), (300, 100, 64),
+                                   (200, 256, 33), (512, 32, 5000), (64, 1, 5), (100, 2, 0)])
+def test_random_vs_oracle(tf, sem, P, W, N):
+    torch, L, B = tf
+    rng = np.random.default_rng(P * 1000 + W + N)
+    world = 64
+    table = random_table(rng, N, world, sem_pf=(sem == "pf"), aabb=True)
+    semc = L.SEM_PF if sem == "pf" else L.SEM_HR
+    env = B.Environment(semc, table, 2.0)
+    pop_h = O.init_walks(P + W, P, W, (32, 32, 32), (0, 0, 0), (63, 63, 63))
+    pop = torch.from_numpy(pop_h).cuda()
+    fit, coll = B.fitness_batch(pop, None, env)
+    oenv = oracle_env_from_table(O.SEM_PF if sem == "pf" else O.SEM_HR, table, 2.0)
+    O.set_threads(8)
+    ofit, ocoll = O.fitness_f32(oenv, pop_h, None, O.default_params(guard=0 if sem == "pf" else 1))
+    O.set_threads(1)
+    assert np.array_equal(ocoll, as_u32(coll))
+    assert np.array_equal(ofit, fit.cpu().numpy())
+
+
+def test_float_inputs_and_ragged_lens(tf):
+    torch, L, B = tf
+    rng = np.random.default_rng(5)
+    P, W, N = 2048, 48, 100
+    table = random_table(rng, N, 32, sem_pf=True)
+    table[:, :3] += rng.uniform(-0.5, 0.5, size=(N, 3))
+    table[:, 3] = rng.uniform(0.5, 3.5, size=N)
+    pop_h = (rng.uniform(0, 32, size=(P, W, 4))).astype(np.float32)
+    lens_h = rng.integers(0, W + 1, size=P).astype(np.int32)
+    for sem, osem in ((L.SEM_PF, O.SEM_PF), (L.SEM_HR, O.SEM_HR)):
+        env = B.Environment(sem, table, 1.5)
+        fit, coll = B.fitness_batch(torch.from_numpy(pop_h).cuda(), torch.from_numpy(lens_h).cuda(), env)
+        oenv = oracle_env_from_table(osem, table, 1.5)
+        ofit, ocoll = O.fitness_f32(oenv, pop_h, lens_h, O.default_params(guard=0 if sem == L.SEM_PF else 1))
+        assert np.array_equal(ocoll, as_u32(coll))
+        assert np.array_equal(ofit, fit.cpu().numpy(), equal_nan=True)
+
+
+def _hazard_field(rng, nt, ny, nx):
+    return rng.uniform(0, 1, size=(nt, ny, nx)).astype(np.float32)
+
+
+def test_voxel_hazard_dynamic_samples(tf):
+    """Extensions (no reference implementation): CUDA == CPU restatement."""
+    torch, L, B = tf
+    rng = np.random.default_rng(11)
+    P, W, N = 3000, 64, 300
+    dims = (64, 64, 32)
+    table = random_table(rng, N, 64, sem_pf=True, max_size=3)
+    table[:, 2] = rng.integers(0, 32, size=N)
+    pop_h = O.init_walks(3, P, W, (32, 32, 16), (0, 0, 0), (63, 63, 31))
+    pop = torch.from_numpy(pop_h).cuda()
+    oenv_an = oracle_env_from_table(O.SEM_PF, table, 0.0)
+    bricks_h = O.voxelize(oenv_an, *dims)
+    bricks = B.voxelize(table, dims, L.SEM_PF)
+    assert np.array_equal(bricks_h, as_u32(bricks)), "voxeliser differs"
+    # (1) voxel-only environment: collision flags == analytic flags on lattice paths
+    env_v = B.Environment.empty().set_voxels(bricks, dims)
+    fit_v, coll_v = B.fitness_batch(pop, None, env_v)
+    env_a = B.Environment(L.SEM_PF, table, 0.0)
+    fit_a, coll_a = B.fitness_batch(pop, None, env_a)
+    assert np.array_equal(as_u32(coll_v), as_u32(coll_a)), "voxel flags must equal analytic flags"
+    ov = O.OracleEnv(O.SEM_NONE, None, bricks=bricks_h, dims=dims)
+    ofit_v, ocoll_v = O.fitness_f32(ov, pop_h, None, O.default_params(guard=1))
+    assert np.array_equal(ocoll_v, as_u32(coll_v)) and np.array_equal(ofit_v, fit_v.cpu().numpy())
+    # (2) everything at once: voxels + moving spheres + hazard map + 3 samples per segment
+    dyn = np.zeros((40, 8), np.float32)
+    dyn[:, :3] = rng.uniform(0, 64, size=(40, 3))
+    dyn[:, 2] = rng.uniform(0, 32, size=40)
+    dyn[:, 3] = rng.integers(1, 4, size=40)
+    dyn[:, 4:7] = rng.uniform(-1, 1, size=(40, 3))
+    haz_h = _hazard_field(rng, 24, 32, 32)
+    hmap = (0.5, 0.5, 0.0, 0.0, 23.0 / (W - 1))
+    env = B.Environment(L.SEM_HR, table, 2.0).set_voxels(bricks, dims).set_dynamic(dyn, 1.0)
+    env.set_hazard(torch.from_numpy(haz_h).cuda(), *hmap)
+    for S in (1, 3):
+        prm = L.default_params(hazard_weight=0.25, samples_per_segment=S)
+        fit, coll = B.fitness_batch(pop, None, env, prm)
+        oe = oracle_env_from_table(O.SEM_HR, table, 2.0, dyn=dyn, dyn_safety=1.0, bricks=bricks_h, dims=dims,
+                                   hazard=haz_h, hazard_map=hmap)
+        O.set_threads(8)
+        ofit, ocoll = O.fitness_f32(oe, pop_h, None, O.default_params(guard=1, hazard_weight=0.25, samples=S))
+        O.set_threads(1)
+        assert np.array_equal(ocoll, as_u32(coll))
+        assert np.array_equal(ofit, fit.cpu().numpy())
+
+
+def test_voxel_pack_linear(tf):
+    torch, L, B = tf
+    rng = np.random.default_rng(2)
+    dims = (32, 16, 24)
+    nbits = dims[0] * dims[1] * dims[2]
+    lin = rng.integers(0, 2 ** 32, size=nbits // 32, dtype=np.uint64).astype(np.uint32)
+    got = B.voxel_pack_linear(torch.from_numpy(lin.view(np.int32)).cuda(), dims)
+    assert np.array_equal(O.voxel_pack_linear(lin, *dims), as_u32(got))
+
+
+def test_error_behaviour(tf):
+    torch, L, B = tf
+    env = B.Environment.empty()
+    with pytest.raises(TypeError):
+        B.fitness_batch(torch.zeros((4, 8, 4)), None, env)          # CPU tensor
+    with pytest.raises(ValueError):
+        B.fitness_batch(torch.zeros((4, 300, 4), device="cuda"), None, env)  # W > TF_W_MAX
+    with pytest.raises(ValueError):
+        B.Environment(7, None, 0.0)
+    fit, coll = B.fitness_batch(torch.zeros((0, 8, 4), device="cuda"), None, env)
+    assert fit.numel() == 0

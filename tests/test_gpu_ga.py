@@ -1,0 +1,193 @@
+"""GPU parity for ranking, selection / crossover / mutation and the fused generation.
+Selected indices, crossover points and the produced populations must be BIT-EXACT:
+  * against the reference itself under its own recorded draw tape (golden evolve traces), and
+  * against the CPU oracle under identical Philox draws (extensions have no reference code)."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as O
+from tests.helpers import as_u32, load_golden, oracle_env_from_table, random_table
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tf():
+    import torch
+    from tracefly_b200 import _lib as L
+    from tracefly_b200 import batched as B
+    assert torch.cuda.is_available()
+    return torch, L, B
+
+
+@pytest.mark.parametrize("P,k", [(1, 1), (7, 7), (100, 10), (2048, 2), (2049, 10), (50_000, 10), (300_000, 1024),
+                                 (1_000_003, 10), (70_000, 7168)])
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_topk_stable_order(tf, P, k, dtype):
+    torch, L, B = tf
+    if dtype == "f64" and k > 4096:
+        pytest.skip("f64 keys: k <= 4096")
+    rng = np.random.default_rng(P + k)
+    # heavy ties (few distinct values) + signed zeros + infinities: the stable order must hold
+    vals = rng.integers(0, max(2, P // 50), size=P).astype(np.float64) / 7.0
+    vals[rng.integers(0, P, size=max(1, P // 100))] = np.inf
+    vals[rng.integers(0, P, size=max(1, P // 100))] = -0.0
+    vals = vals.astype(np.float32 if dtype == "f32" else np.float64)
+    fit = torch.from_numpy(vals).cuda()
+    for worst in (False, True):
+        got = B.rank_topk(fit, k, worst=worst).cpu().numpy()
+        assert np.array_equal(got, O.topk(vals, k, worst=worst))
+
+
+def test_all_equal_population_keeps_index_order(tf):
+    """Generation 0 of HR is P identical paths (HR:82-83): the stable sort must return 0..k-1."""
+    torch, L, B = tf
+    fit = torch.full((5000,), 0.625, device="cuda")
+    assert B.rank_topk(fit, 10).cpu().tolist() == list(range(10))
+    assert B.rank_topk(fit, 3, worst=True).cpu().tolist() == [4999, 4998, 4997]
+
+
+@pytest.mark.parametrize("name", ["tiny", "odd_hot", "default", "cfg1"])
+def test_ga_step_replays_reference_generations(tf, name):
+    """Each recorded generation of the unmodified reference: rank -> tape-driven GA step must
+    reproduce the next population bit for bit, and the FP64 kernel its fitness bit for bit."""
+    torch, L, B = tf
+    g, meta = load_golden(f"evolve_hr_{name}.npz")
+    P, G, W = meta["P"], meta["G"], meta["W"]
+    table = np.zeros((len(g["obs_pos"]), 8))
+    table[:, :3] = g["obs_pos"]
+    table[:, 3] = np.where(np.isnan(g["obs_size"]), -1.0, g["obs_size"])
+    env = B.Environment(L.SEM_HR, table, 2.0)
+    pops = np.zeros((G + 1, P, W, 4))
+    pops[..., :3] = g["pops"]
+    ga = L.default_ga_params(mutation_rate=meta["rate"])
+    k = min(10, P)
+    gens = range(G) if G <= 40 else list(range(0, G, 7)) + [G - 1]
+    for gen in gens:
+        pop = torch.from_numpy(pops[gen]).cuda()
+        fit = torch.from_numpy(g["fits"][gen]).cuda()
+        top = B.rank_topk(fit, k)
+        order = np.lexsort((np.arange(P), -g["fits"][gen]))
+        assert np.array_equal(top.cpu().numpy(), order[:k])
+        nxt, _, sel, cp = B.ga_step(pop, fit, top, ga, tape=g["tape"][gen])
+        assert np.array_equal(nxt.cpu().numpy(), pops[gen + 1]), f"generation {gen}: population differs"
+        assert np.array_equal(cp.cpu().numpy(), g["tape"][gen][:, 2])
+        assert np.array_equal(sel.cpu().numpy(), order[:k][g["tape"][gen][:, :2]])
+        f64, _ = B.fitness_batch_f64(nxt, None, env)
+        assert np.array_equal(f64.cpu().numpy(), g["fits"][gen + 1]), f"generation {gen}: fitness differs"
+
+
+COMBOS = [
+    dict(selection=0, crossover=0, mutation=0),   # the reference's own operators, Philox draws
+    dict(selection=1, crossover=0, mutation=0, tournament_k=4),
+    dict(selection=1, crossover=1, mutation=2, tournament_k=7, sigma=0.75),
+    dict(selection=0, crossover=1, mutation=1, n_top=32),
+    dict(selection=1, crossover=0, mutation=1, tournament_k=32, n_elite=5),
+    dict(selection=1, crossover=0, mutation=0, tournament_k=1, n_elite=0),
+]
+
+
+@pytest.mark.parametrize("combo", COMBOS)
+@pytest.mark.parametrize("P,W", [(1001, 20), (4096, 64), (513, 100)])
+def test_ga_step_philox_vs_oracle(tf, combo, P, W):
+    torch, L, B = tf
+    rng = np.random.default_rng(P + W)
+    pop_h = O.init_walks(9, P, W, (32, 32, 32), (0, 0, 0), (63, 63, 63))
+    fit_h = rng.integers(0, 300, size=P).astype(np.float32) / 301.0   # ties included
+    kw = dict(mutation_rate=0.4, stream_id=3)
+    kw.update(combo)
+    ga, oga = L.default_ga_params(**kw), O.default_ga(**kw)
+    k = max(min(ga.n_elite, P), ga.n_top if ga.selection == 0 else 1, 1)
+    pop, fit = torch.from_numpy(pop_h).cuda(), torch.from_numpy(fit_h).cuda()
+    top = B.rank_topk(fit, k)
+    otop = O.topk(fit_h, k)
+    assert np.array_equal(otop, top.cpu().numpy())
+    nxt, _, sel, cp = B.ga_step(pop, fit, top, ga, seed=0xDEADBEEFCAFE, generation=17)
+    onxt, _, osel, ocp = O.ga_step(pop_h, fit_h, otop, oga, seed=0xDEADBEEFCAFE, gen=17)
+    assert np.array_equal(osel, sel.cpu().numpy()), "selected parent indices differ"
+    assert np.array_equal(ocp, cp.cpu().numpy()), "crossover points differ"
+    assert np.array_equal(onxt, nxt.cpu().numpy()), "children differ"
+    if ga.n_elite:
+        assert np.array_equal(nxt[:ga.n_elite].cpu().numpy(), pop_h[otop[:ga.n_elite]])
+
+
+def test_ga_step_variable_lengths(tf):
+    """PF/GAE populations are ragged: child1 = p1[:cp] + p2[cp:] has len(p2)."""
+    torch, L, B = tf
+    rng = np.random.default_rng(3)
+    P, W = 600, 40
+    pop_h = O.init_walks(4, P, W, (32, 32, 32), (0, 0, 0), (63, 63, 63))
+    lens_h = rng.integers(3, W + 1, size=P).astype(np.int32)
+    fit_h = rng.random(P).astype(np.float32)
+    for mut in (0, 1):
+        ga, oga = L.default_ga_params(mutation=mut, mutation_rate=0.5), O.default_ga(mutation=mut, mutation_rate=0.5)
+        pop, fit, lens = torch.from_numpy(pop_h).cuda(), torch.from_numpy(fit_h).cuda(), torch.from_numpy(lens_h).cuda()
+        top = B.rank_topk(fit, 10)
+        nxt, nlens, sel, cp = B.ga_step(pop, fit, top, ga, seed=5, generation=2, lens=lens)
+        onxt, onlens, osel, ocp = O.ga_step(pop_h, fit_h, O.topk(fit_h, 10), oga, seed=5, gen=2, lens=lens_h)
+        assert np.array_equal(onlens, nlens.cpu().numpy())
+        assert np.array_equal(osel, sel.cpu().numpy()) and np.array_equal(ocp, cp.cpu().numpy())
+        assert np.array_equal(onxt, nxt.cpu().numpy())
+
+
+@pytest.mark.parametrize("combo", COMBOS[:4])
+@pytest.mark.parametrize("sem,W,N", [("hr", 20, 10), ("pf", 32, 1024), ("pf", 64, 200), ("none", 100, 0)])
+def test_fused_generation_equals_unfused_and_oracle(tf, combo, sem, W, N):
+    torch, L, B = tf
+    P = 3001
+    rng = np.random.default_rng(W + N)
+    semc = {"hr": L.SEM_HR, "pf": L.SEM_PF, "none": L.SEM_NONE}[sem]
+    table = random_table(rng, N, 64, sem_pf=(sem == "pf"))
+    env = B.Environment(semc, table, 2.0)
+    pop_h = O.init_walks(21, P, W, (32, 32, 32), (0, 0, 0), (63, 63, 63))
+    pop = torch.from_numpy(pop_h).cuda()
+    fit, _ = B.fitness_batch(pop, None, env)
+    kw = dict(mutation_rate=0.3)
+    kw.update(combo)
+    ga = L.default_ga_params(**kw)
+    k = max(min(ga.n_elite, P), ga.n_top if ga.selection == 0 else 1, 1)
+    top = B.rank_topk(fit, k)
+    nxt_f, fit_f, coll_f, sel_f, cp_f = B.generation(env, pop, fit, top, ga, seed=99, generation=5,
+                                                     want_collisions=True, want_parity=True)
+    nxt_u, _, sel_u, cp_u = B.ga_step(pop, fit, top, ga, seed=99, generation=5)
+    fit_u, coll_u = B.fitness_batch(nxt_u, None, env)
+    assert torch.equal(nxt_f, nxt_u) and torch.equal(fit_f, fit_u) and torch.equal(coll_f, coll_u)
+    assert torch.equal(sel_f, sel_u) and torch.equal(cp_f, cp_u)
+    oenv = oracle_env_from_table({"hr": O.SEM_HR, "pf": O.SEM_PF, "none": O.SEM_NONE}[sem], table, 2.0)
+    fit_h = fit.cpu().numpy()
+    onxt, _, osel, ocp = O.ga_step(pop_h, fit_h, O.topk(fit_h, k), O.default_ga(**kw), seed=99, gen=5)
+    O.set_threads(8)
+    ofit, ocoll = O.fitness_f32(oenv, onxt, None, O.default_params(guard=0 if sem == "pf" else 1))
+    O.set_threads(1)
+    assert np.array_equal(onxt, nxt_f.cpu().numpy()) and np.array_equal(osel, sel_f.cpu().numpy())
+    assert np.array_equal(ofit, fit_f.cpu().numpy()) and np.array_equal(ocoll, as_u32(coll_f))
+
+
+def test_track_best_lag_quirk(tf):
+    """HR:126-128: best follows population[0] (last generation's elite) with a strict '>'."""
+    torch, L, B = tf
+    W = 8
+    tr = B.BestTracker(W)
+    pop = torch.arange(3 * W * 4, dtype=torch.float32, device="cuda").reshape(3, W, 4)
+    for gen, f0 in enumerate([0.5, 0.5, 0.7, 0.6]):
+        fit = torch.tensor([f0, 9.0, 9.0], device="cuda")
+        tr.update(pop + gen, fit, 0, gen)
+    assert float(tr.best_fit) == pytest.approx(0.7) and int(tr.best_gen) == 2
+    assert torch.equal(tr.best_path, (pop + 2)[0])
+
+
+def test_init_populations(tf):
+    torch, L, B = tf
+    for start, end in [((0, 0, 0), (15, 15, 8)), ((0, 0, 0), (19, 19, 8)), ((2, 1, 0), (9, 12, 4)),
+                       ((0.0, 0.0, 0.0), (2.886751345948129, 2.886751345948129, 0.7698003589195010)), ((3, 3, 3), (3, 3, 3))]:
+        ref = O.init_diagonal(start, end)
+        pop, n = B.init_diagonal(start, end, 37, f64=True)
+        assert n == len(ref)
+        assert np.array_equal(pop.cpu().numpy(), np.repeat(ref[None], 37, axis=0))
+        pop32, _ = B.init_diagonal(start, end, 5)
+        assert np.array_equal(pop32.cpu().numpy(), np.repeat(ref[None], 5, axis=0).astype(np.float32))
+    starts = torch.rand((1000, 4), device="cuda") * 50
+    starts = starts.floor()
+    got = B.init_walks(77, 1000, 33, lo=(0, 0, 0), hi=(49, 49, 49), start_per_path=starts)
+    exp = O.init_walks(77, 1000, 33, (0, 0, 0), (0, 0, 0), (49, 49, 49), start_pp=starts.cpu().numpy())
+    assert np.array_equal(exp, got.cpu().numpy())

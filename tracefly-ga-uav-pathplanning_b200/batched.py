@@ -1,0 +1,389 @@
+"""Array-form entry points of the GA hot path ("chromosome-as-waypoint-array in, fitness vector
+and next population out", BASELINE.json north_star).  torch is used for device memory and
+streams only; every computation is a call through the C-ABI of libtracefly_b200.so.
+
+Layouts: population f32[P, W, 4] (x, y, z, pad) on the GPU, fitness f32[P],
+collision flags u32[P, ceil(W/32)] (returned as int32 tensors; bit i of word k = waypoint 32k+i).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from ._lib import check, lib
+
+KINDS = {"sphere": L.KIND_SPHERE, "cube": L.KIND_CUBE, "cylinder": L.KIND_CYLINDER, "aabb": L.KIND_AABB}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("tracefly_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk_tensor(t, dtype, name, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} dims")
+
+
+class Environment:
+    """Device-side obstacle set: analytic obstacles (HR or PF rules), optional moving spheres,
+    optional bit-packed voxel grid, optional hazard heat-map.  Owns a tf_env."""
+
+    def __init__(self, semantics=L.SEM_NONE, table64=None, safety_radius=2.0):
+        _require_cuda()
+        self.semantics = semantics
+        self.safety_radius = float(safety_radius)
+        t = np.zeros((0, 8), np.float64) if table64 is None else np.ascontiguousarray(table64, np.float64)
+        self.table64 = t
+        self._h = C.c_void_p()
+        check(lib.tf_env_create_f64(semantics, t.ctypes.data_as(C.c_void_p), len(t), self.safety_radius,
+                                    C.byref(self._h)), "tf_env_create_f64")
+        self._keep = {}
+
+    # ---- constructors mirroring the reference's obstacle formats
+    @classmethod
+    def from_hr_obstacles(cls, obstacles, safety_radius=2.0):
+        """obstacles: list of {"position": [x,y,z], "size": s?} (detected_objects.json, HR:10-15).
+        A missing size stays missing (-1) and takes the HR:20 default 1.0 on the device."""
+        t = np.zeros((len(obstacles), 8), np.float64)
+        for i, o in enumerate(obstacles):
+            t[i, 0:3] = np.asarray(o["position"], np.float64)[:3]
+            t[i, 3] = float(o["size"]) if "size" in o else -1.0
+        return cls(L.SEM_HR, t, safety_radius)
+
+    @classmethod
+    def from_pf_obstacles(cls, obstacles):
+        """obstacles: list of {"shape", "position", "size"} (ComplexEnvironment.obstacles, PF:17-26);
+        an "aabb" shape with "half": (hx,hy,hz) is accepted as an extension."""
+        t = np.zeros((len(obstacles), 8), np.float64)
+        for i, o in enumerate(obstacles):
+            t[i, 0:3] = np.asarray(o["position"], np.float64)[:3]
+            t[i, 3] = float(o["size"])
+            t[i, 7] = KINDS[o["shape"]]
+            if o["shape"] == "aabb":
+                t[i, 4:7] = np.asarray(o["half"], np.float64)
+        return cls(L.SEM_PF, t, 0.0)
+
+    @classmethod
+    def empty(cls):
+        return cls(L.SEM_NONE, None, 0.0)
+
+    # ---- optional attachments
+    def set_dynamic(self, dyn, safety_radius=2.0):
+        """dyn: float array [n, 7|8] = cx cy cz size vx vy vz — moving spheres (extension)."""
+        d = np.zeros((len(dyn), 8), np.float32)
+        d[:, :7] = np.asarray(dyn, np.float32)[:, :7]
+        check(lib.tf_env_set_dynamic(self._h, d.ctypes.data_as(C.c_void_p), len(d), float(safety_radius)),
+              "tf_env_set_dynamic")
+        return self
+
+    def set_voxels(self, bricks, dims):
+        """bricks: int32/uint32 CUDA tensor in brick layout (see voxelize / voxel_pack_linear)."""
+        if bricks is None:
+            check(lib.tf_env_set_voxels(self._h, None, 0, 0, 0), "tf_env_set_voxels")
+            self._keep.pop("bricks", None)
+            return self
+        nx, ny, nz = dims
+        need = lib.tf_voxel_grid_bytes(nx, ny, nz)
+        if need < 0 or bricks.numel() * bricks.element_size() != need or not bricks.is_cuda:
+            raise ValueError("bricks must be a CUDA tensor of tf_voxel_grid_bytes(nx,ny,nz) bytes")
+        check(lib.tf_env_set_voxels(self._h, _ptr(bricks), nx, ny, nz), "tf_env_set_voxels")
+        self._keep["bricks"] = bricks
+        return self
+
+    def set_hazard(self, hazard, sx=1.0, sy=1.0, ox=0.0, oy=0.0, st=1.0):
+        """hazard: f32[nt, ny, nx] CUDA tensor; waypoint i at (x, y) samples (x*sx+ox, y*sy+oy, i*st)."""
+        if hazard is None:
+            check(lib.tf_env_set_hazard(self._h, None, 0, 0, 0, 1, 1, 0, 0, 1), "tf_env_set_hazard")
+            self._keep.pop("hazard", None)
+            return self
+        _chk_tensor(hazard, torch.float32, "hazard", 3)
+        nt, ny, nx = hazard.shape
+        check(lib.tf_env_set_hazard(self._h, _ptr(hazard), nt, ny, nx, sx, sy, ox, oy, st), "tf_env_set_hazard")
+        self._keep["hazard"] = hazard
+        return self
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib.tf_env_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------ voxels
+def voxel_grid_words(nx, ny, nz):
+    b = lib.tf_voxel_grid_bytes(nx, ny, nz)
+    if b < 0:
+        raise ValueError("voxel grid dims must be positive multiples of 8")
+    return b // 4
+
+
+def obstacle_records(table):
+    """float table [n, 8] (cx cy cz size hx hy hz kind) -> tf_obstacle records as a uint8 CPU tensor."""
+    t = np.asarray(table, np.float64)
+    rec = np.zeros((len(t), 8), np.float32)
+    rec[:, :7] = t[:, :7]
+    rec[:, 7] = t[:, 7].astype(np.int32).view(np.float32)
+    return torch.from_numpy(rec)
+
+
+def voxelize(table, dims, semantics=L.SEM_PF, safety_radius=0.0, out=None):
+    """Rasterise analytic obstacles into a brick-layout occupancy grid on the GPU."""
+    _require_cuda()
+    nx, ny, nz = dims
+    words = voxel_grid_words(nx, ny, nz)
+    if out is None:
+        out = torch.zeros(words, dtype=torch.int32, device="cuda")
+    rec = obstacle_records(table).cuda()
+    check(lib.tf_voxelize(semantics, _ptr(rec), rec.shape[0], float(safety_radius), _ptr(out), nx, ny, nz, _stream()),
+          "tf_voxelize")
+    return out
+
+
+def voxel_pack_linear(linear, dims):
+    """linear: int32 CUDA tensor, bit index x + nx*(y + ny*z) -> brick layout."""
+    nx, ny, nz = dims
+    out = torch.empty(voxel_grid_words(nx, ny, nz), dtype=torch.int32, device="cuda")
+    check(lib.tf_voxel_pack_linear(_ptr(linear), _ptr(out), nx, ny, nz, _stream()), "tf_voxel_pack_linear")
+    return out
+
+
+# ------------------------------------------------------------------------------------ fitness
+def fitness_batch(pop, lens, env, params=None, out=None, want_collisions=True):
+    """Path.calculate_fitness (HR:42-59 / PF:144-170) for a whole population (FP32 kernel).
+    pop f32[P,W,4] cuda; lens i32[P] cuda or None.  -> (fitness f32[P], collide i32[P, ceil(W/32)])"""
+    _chk_tensor(pop, torch.float32, "pop", 3)
+    P, W, four = pop.shape
+    if four != 4:
+        raise ValueError("pop must be [P, W, 4]")
+    if lens is not None:
+        _chk_tensor(lens, torch.int32, "lens", 1)
+    params = params or L.default_params(dist_zero_guard=1 if env.semantics != L.SEM_PF else 0)
+    fit = out if out is not None else torch.empty(P, dtype=torch.float32, device=pop.device)
+    coll = torch.empty((P, (W + 31) // 32), dtype=torch.int32, device=pop.device) if want_collisions else None
+    check(lib.tf_fitness(env.handle, _ptr(pop), _ptr(lens), P, W, C.byref(params), _ptr(fit), _ptr(coll), _stream()),
+          "tf_fitness")
+    return fit, coll
+
+
+def fitness_batch_f64(pop64, lens, env, params=None, out=None, want_collisions=True):
+    """Reference-order float64 fitness: bit-identical to the reference on identical inputs."""
+    _chk_tensor(pop64, torch.float64, "pop64", 3)
+    P, W, _ = pop64.shape
+    if lens is not None:
+        _chk_tensor(lens, torch.int32, "lens", 1)
+    params = params or L.default_params(dist_zero_guard=1 if env.semantics != L.SEM_PF else 0)
+    fit = out if out is not None else torch.empty(P, dtype=torch.float64, device=pop64.device)
+    coll = torch.empty((P, (W + 31) // 32), dtype=torch.int32, device=pop64.device) if want_collisions else None
+    check(lib.tf_fitness_f64(env.handle, _ptr(pop64), _ptr(lens), P, W, C.byref(params), _ptr(fit), _ptr(coll),
+                             _stream()), "tf_fitness_f64")
+    return fit, coll
+
+
+def point_query_f64(points, env):
+    """is_collision / distance_to_nearest_obstacle (HR:17-28) or is_obstacle / distance_to_obstacles
+    (PF:28-59) for a batch of points, float64 reference arithmetic.  points: array-like [n, 3].
+    -> (collide bool[n] numpy, dnear f64[n] numpy)"""
+    _require_cuda()
+    pts = np.zeros((len(points), 4), np.float64)
+    if len(points):
+        pts[:, :3] = np.asarray(points, np.float64).reshape(len(points), -1)[:, :3]
+    d = torch.from_numpy(pts).cuda()
+    n = len(pts)
+    coll = torch.empty(n, dtype=torch.int32, device="cuda")
+    dn = torch.empty(n, dtype=torch.float64, device="cuda")
+    check(lib.tf_point_query_f64(env.handle, _ptr(d), n, _ptr(coll), _ptr(dn), _stream()), "tf_point_query_f64")
+    return coll.cpu().numpy().astype(bool), dn.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------ ranking
+class TopK:
+    """Reusable top-k plan (owns the workspace): order = (fitness desc, index asc) — the stable
+    descending sort of HR:114.  worst=True returns the tail of that order, worst first."""
+
+    def __init__(self, P, k, f64=False, device="cuda"):
+        self.P, self.k, self.f64 = P, k, f64
+        nbytes = lib.tf_topk_workspace_bytes(P, k, int(f64))
+        if nbytes < 0:
+            raise ValueError(f"top-k: unsupported P={P}, k={k}")
+        self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        self.nbytes = int(nbytes)
+
+    def __call__(self, fit, worst=False, out=None):
+        idx = out if out is not None else torch.empty(self.k, dtype=torch.int32, device=fit.device)
+        fn = lib.tf_rank_topk_f64 if self.f64 else lib.tf_rank_topk
+        _chk_tensor(fit, torch.float64 if self.f64 else torch.float32, "fit", 1)
+        check(fn(_ptr(fit), self.P, self.k, int(worst), _ptr(idx), _ptr(self.ws), self.nbytes, _stream()), "tf_rank_topk")
+        return idx
+
+
+def rank_topk(fit, k, worst=False):
+    return TopK(fit.numel(), k, f64=fit.dtype == torch.float64, device=fit.device)(fit, worst)
+
+
+# ------------------------------------------------------------------------------------ GA step
+def _as_tape(tape, device):
+    if tape is None:
+        return None
+    if isinstance(tape, np.ndarray):
+        tape = torch.from_numpy(np.ascontiguousarray(tape, np.int32)).to(device)
+    _chk_tensor(tape, torch.int32, "tape", 2)
+    if tape.shape[1] != 8:
+        raise ValueError("tape must be int32[npairs, 8] (tf_draw records)")
+    return tape
+
+
+def ga_step(pop, fit, top_idx, ga=None, tape=None, seed=0, generation=0, lens=None, out=None, want_parity=True):
+    """Selection + crossover + mutation (HR:114-122).  pop f32 or f64 [P,W,4].
+    -> (next_pop, next_lens or None, sel i32[npairs,2] or None, cp i32[npairs] or None)"""
+    ga = ga or L.default_ga_params()
+    f64 = pop.dtype == torch.float64
+    _chk_tensor(pop, torch.float64 if f64 else torch.float32, "pop", 3)
+    P, W, _ = pop.shape
+    ne = min(ga.n_elite, P)
+    npairs = (P - ne + 1) // 2
+    tape = _as_tape(tape, pop.device)
+    if tape is not None and tape.shape[0] < npairs:
+        raise ValueError("tape shorter than the number of child pairs")
+    nxt = out if out is not None else torch.empty_like(pop)
+    next_lens = torch.empty(P, dtype=torch.int32, device=pop.device) if lens is not None else None
+    sel = torch.empty((npairs, 2), dtype=torch.int32, device=pop.device) if want_parity else None
+    cp = torch.empty(npairs, dtype=torch.int32, device=pop.device) if want_parity else None
+    fn = lib.tf_ga_step_f64 if f64 else lib.tf_ga_step
+    check(fn(_ptr(pop), _ptr(lens), _ptr(fit), _ptr(top_idx), _ptr(tape), seed, generation, C.byref(ga), P, W,
+             _ptr(nxt), _ptr(next_lens), _ptr(sel), _ptr(cp), _stream()), "tf_ga_step")
+    return nxt, next_lens, sel, cp
+
+
+def generation(env, pop, fit, top_idx, ga=None, params=None, tape=None, seed=0, generation=0, out_pop=None,
+               out_fit=None, want_collisions=False, want_parity=False):
+    """Fused GA step + fitness sweep (FP32, fixed W): the child never round-trips through HBM.
+    -> (next_pop, next_fit, next_coll or None, sel or None, cp or None)"""
+    ga = ga or L.default_ga_params()
+    _chk_tensor(pop, torch.float32, "pop", 3)
+    P, W, _ = pop.shape
+    params = params or L.default_params(dist_zero_guard=1 if env.semantics != L.SEM_PF else 0)
+    ne = min(ga.n_elite, P)
+    npairs = (P - ne + 1) // 2
+    tape = _as_tape(tape, pop.device)
+    nxt = out_pop if out_pop is not None else torch.empty_like(pop)
+    nfit = out_fit if out_fit is not None else torch.empty(P, dtype=torch.float32, device=pop.device)
+    coll = torch.empty((P, (W + 31) // 32), dtype=torch.int32, device=pop.device) if want_collisions else None
+    sel = torch.empty((npairs, 2), dtype=torch.int32, device=pop.device) if want_parity else None
+    cp = torch.empty(npairs, dtype=torch.int32, device=pop.device) if want_parity else None
+    check(lib.tf_generation(env.handle, _ptr(pop), _ptr(fit), _ptr(top_idx), _ptr(tape), seed, generation,
+                            C.byref(ga), C.byref(params), P, W, _ptr(nxt), _ptr(nfit), _ptr(coll), _ptr(sel), _ptr(cp),
+                            _stream()), "tf_generation")
+    return nxt, nfit, coll, sel, cp
+
+
+# ------------------------------------------------------------------------------------ initial populations
+def init_diagonal(start, end, P, f64=False, W=None):
+    """HR:68-83: the diagonal lattice walk start -> end replicated P times.  -> pop [P, W, 4]"""
+    _require_cuda()
+    s = (C.c_double * 3)(*[float(v) for v in start])
+    e = (C.c_double * 3)(*[float(v) for v in end])
+    n = C.c_int(0)
+    fn = lib.tf_init_diagonal_f64 if f64 else lib.tf_init_diagonal
+    check(fn(s, e, 0, 0, None, C.byref(n), None), "tf_init_diagonal(size)")
+    W = n.value if W is None else W
+    pop = torch.zeros((P, W, 4), dtype=torch.float64 if f64 else torch.float32, device="cuda")
+    check(fn(s, e, P, W, _ptr(pop), C.byref(n), _stream()), "tf_init_diagonal")
+    return pop, n.value
+
+
+def init_walks(seed, P, W, start=(0, 0, 0), lo=(-1e30,) * 3, hi=(1e30,) * 3, start_per_path=None):
+    """Seeded +-1 lattice random walks (the synthetic populations of BASELINE configs[1..4])."""
+    _require_cuda()
+    pop = torch.empty((P, W, 4), dtype=torch.float32, device="cuda")
+    f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])
+    if start_per_path is not None:
+        _chk_tensor(start_per_path, torch.float32, "start_per_path", 2)
+    check(lib.tf_init_walks(seed, _ptr(start_per_path), f3(start), f3(lo), f3(hi), P, W, _ptr(pop), _stream()),
+          "tf_init_walks")
+    return pop
+
+
+# ------------------------------------------------------------------------------------ evolve
+class BestTracker:
+    """HR:126-128 on the device: best <- pop[slot] whenever fit[slot] > best_fit."""
+
+    def __init__(self, W, f64=False, device="cuda"):
+        dt = torch.float64 if f64 else torch.float32
+        self.f64 = f64
+        self.W = W
+        self.best_fit = torch.full((1,), -1.0, dtype=dt, device=device)  # HR:107
+        self.best_path = torch.zeros((W, 4), dtype=dt, device=device)
+        self.best_gen = torch.full((1,), -1, dtype=torch.int32, device=device)
+
+    def update(self, pop, fit, slot, generation):
+        fn = lib.tf_track_best_f64 if self.f64 else lib.tf_track_best
+        check(fn(_ptr(pop), _ptr(fit), slot, self.W, generation, _ptr(self.best_fit), _ptr(self.best_path),
+                 _ptr(self.best_gen), _stream()), "tf_track_best")
+
+
+def evolve_batch(pop, env, generations, ga=None, params=None, seed=0, tapes=None, fused=True, start_generation=0,
+                 should_stop=None, record_best=True, inplace=False):
+    """Runs `generations` GA generations on the device (HR:109-128 generalised):
+    rank -> (select, crossover, mutate) -> fitness, with HR's best tracking.
+    tapes: optional int32[G, npairs, 8] host draws (np.random order, HR:118-120); else Philox.
+    Returns dict(pop, fit, best_path [W,4], best_fit, best_gen)."""
+    ga = ga or L.default_ga_params()
+    f64 = pop.dtype == torch.float64
+    P, W, _ = pop.shape
+    params = params or L.default_params(dist_zero_guard=1 if env.semantics != L.SEM_PF else 0)
+    k = max(min(ga.n_elite, P), min(ga.n_top, P) if ga.selection == L.SEL_TRUNCATION else 1, 1)
+    topk = TopK(P, k, f64=f64, device=pop.device)
+    tracker = BestTracker(W, f64=f64, device=pop.device) if record_best else None
+    fit = (fitness_batch_f64(pop, None, env, params) if f64 else fitness_batch(pop, None, env, params, want_collisions=False))[0]
+    cur, nxt = (pop if inplace else pop.clone()), torch.empty_like(pop)  # ping-pong buffers
+    nfit = torch.empty_like(fit)
+    top = torch.empty(k, dtype=torch.int32, device=pop.device)
+    if tapes is not None and isinstance(tapes, np.ndarray):
+        tapes = torch.from_numpy(np.ascontiguousarray(tapes, np.int32)).to(pop.device)
+    for g in range(generations):
+        if should_stop is not None and should_stop():
+            return None
+        topk(fit, out=top)
+        tape = None if tapes is None else tapes[g]
+        gen_no = start_generation + g
+        if f64 or not fused:
+            ga_step(cur, fit, top, ga, tape=tape, seed=seed, generation=gen_no, out=nxt, want_parity=False)
+            if f64:
+                fitness_batch_f64(nxt, None, env, params, out=nfit, want_collisions=False)
+            else:
+                fitness_batch(nxt, None, env, params, out=nfit, want_collisions=False)
+        else:
+            generation(env, cur, fit, top, ga, params, tape=tape, seed=seed, generation=gen_no, out_pop=nxt, out_fit=nfit)
+        cur, nxt = nxt, cur
+        fit, nfit = nfit, fit
+        if tracker is not None:
+            tracker.update(cur, fit, 0, gen_no)
+    out = dict(pop=cur, fit=fit)
+    if tracker is not None:
+        out.update(best_path=tracker.best_path, best_fit=tracker.best_fit, best_gen=tracker.best_gen)
+    return out

@@ -1,0 +1,325 @@
+// tf_env.cu — environment objects (obstacle tables, voxel grid, hazard map), the voxeliser,
+// and the small misc entry points of the C-ABI.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "tf_common.cuh"
+
+namespace tf {
+
+thread_local int g_last_cuda_error = 0;
+long long g_launch_count = 0;
+static int g_sm_count = 0;
+static int g_dev_checked = 0;
+
+int ensure_device() {
+    if (g_dev_checked) return g_dev_checked > 0 ? TF_OK : TF_ERR_NODEVICE;
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        cudaGetLastError();
+        g_dev_checked = -1;  // no sm_100 device: there is deliberately no fallback
+        return TF_ERR_NODEVICE;
+    }
+    g_sm_count = prop.multiProcessorCount;
+    g_dev_checked = 1;
+    return TF_OK;
+}
+int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+
+// ------------------------------------------------------------------ voxel kernels
+__device__ __forceinline__ size_t brick_word(int x, int y, int z, int nbx, int nby) {
+    size_t b = (size_t)(x >> 3) + (size_t)nbx * ((size_t)(y >> 3) + (size_t)nby * (size_t)(z >> 3));
+    return b * 16 + ((z & 7) * 2 + ((y & 7) >> 2));
+}
+
+// One warp per obstacle: walk its bounding box, set the bit of every colliding lattice point.
+// Collision rules and arithmetic are those of the FP32 fitness model (HR:17-23 / PF:28-44).
+__global__ void voxelize_kernel(int semantics, const tf_obstacle* __restrict__ obs, int n, float safety,
+                                uint32_t* __restrict__ bricks, int nx, int ny, int nz) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const tf_obstacle o = obs[w];
+    const float s = o.size < 0.0f ? 1.0f : o.size;
+    float rx = s, ry = s, rz = s;
+    if (semantics == TF_SEM_HR) rx = ry = rz = __fadd_rn(s, safety);
+    else if (o.kind == TF_KIND_CYLINDER) rz = __fmul_rn(2.0f, s);
+    else if (o.kind == TF_KIND_AABB) { rx = o.hx; ry = o.hy; rz = o.hz; }
+    const int x0 = max(0, (int)floorf(o.cx - rx)), x1 = min(nx - 1, (int)ceilf(o.cx + rx));
+    const int y0 = max(0, (int)floorf(o.cy - ry)), y1 = min(ny - 1, (int)ceilf(o.cy + ry));
+    const int z0 = max(0, (int)floorf(o.cz - rz)), z1 = min(nz - 1, (int)ceilf(o.cz + rz));
+    if (x1 < x0 || y1 < y0 || z1 < z0) return;
+    const int ex = x1 - x0 + 1, ey = y1 - y0 + 1, ez = z1 - z0 + 1;
+    const long long total = (long long)ex * ey * ez;
+    const float r = __fadd_rn(s, safety), r2 = __fmul_rn(r, r), s2 = __fmul_rn(s, s);
+    for (long long i = lane; i < total; i += 32) {
+        const int x = x0 + (int)(i % ex), y = y0 + (int)((i / ex) % ey), z = z0 + (int)(i / ((long long)ex * ey));
+        const float dx = (float)x - o.cx, dy = (float)y - o.cy, dz = (float)z - o.cz;
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
+        bool hit;
+        if (semantics == TF_SEM_HR) hit = d2 <= r2;
+        else if (o.kind == TF_KIND_SPHERE) hit = d2 <= s2;
+        else hit = fabsf(dx) <= rx && fabsf(dy) <= ry && fabsf(dz) <= rz;
+        if (hit) atomicOr(bricks + brick_word(x, y, z, nx >> 3, ny >> 3), 1u << (((y & 3) << 3) | (x & 7)));
+    }
+}
+
+// One thread per brick word: gathers its 8x4 voxels from the linear bit grid.
+__global__ void pack_linear_kernel(const uint32_t* __restrict__ lin, uint32_t* __restrict__ bricks, int nx, int ny,
+                                   int nz, size_t nwords) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    const int nbx = nx >> 3, nby = ny >> 3;
+    const size_t brick = i >> 4;
+    const int wi = (int)(i & 15);
+    const int bx = (int)(brick % nbx), by = (int)((brick / nbx) % nby), bz = (int)(brick / ((size_t)nbx * nby));
+    const int z = bz * 8 + (wi >> 1), ybase = by * 8 + (wi & 1) * 4, xbase = bx * 8;
+    uint32_t out = 0;
+#pragma unroll
+    for (int yy = 0; yy < 4; ++yy) {
+        const size_t bit0 = (size_t)xbase + (size_t)nx * ((size_t)(ybase + yy) + (size_t)ny * z);  // multiple of 8
+        const uint32_t byte = (lin[bit0 >> 5] >> (bit0 & 31)) & 0xffu;
+        out |= byte << (yy * 8);
+    }
+    bricks[i] = out;
+}
+
+}  // namespace tf
+
+using namespace tf;
+
+// ------------------------------------------------------------------ env lifecycle
+static int upload_static(tf_env* env, int semantics, const std::vector<double>& obs64, int n, double safety) {
+    // kind-sort (stable) and pre-square for the FP32 tables
+    std::vector<int> order;
+    int cnt[4] = {0, 0, 0, 0};
+    if (semantics == TF_SEM_PF) {
+        for (int kind = 0; kind < 4; ++kind)
+            for (int i = 0; i < n; ++i) {
+                int k = (int)obs64[8 * i + 7];
+                if (k < 0 || k > 3) return TF_ERR_INVALID;
+                if (k == kind) { order.push_back(i); ++cnt[kind]; }
+            }
+    } else {
+        for (int i = 0; i < n; ++i) order.push_back(i);
+        cnt[0] = n;
+    }
+    std::vector<float> A((size_t)n * 4), B((size_t)n * 4, 0.0f);
+    for (int j = 0; j < n; ++j) {
+        const double* o = &obs64[8 * order[j]];
+        A[4 * j] = (float)o[0]; A[4 * j + 1] = (float)o[1]; A[4 * j + 2] = (float)o[2];
+        if (semantics == TF_SEM_HR) {
+            float size = (float)o[3] < 0.0f ? 1.0f : (float)o[3];  // HR:20 default size 1.0
+            float r = size + (float)safety;
+            A[4 * j + 3] = r * r;  // compared against d^2 (numerics)
+        } else {
+            A[4 * j + 3] = (float)o[3];
+            B[4 * j] = (float)o[4]; B[4 * j + 1] = (float)o[5]; B[4 * j + 2] = (float)o[6];
+        }
+    }
+    size_t bytesA = (size_t)n * 16, bytes64 = (size_t)n * 64;
+    void* block = nullptr;
+    if (n > 0) {
+        TF_CUDA(cudaMalloc(&block, bytesA * 2 + bytes64));
+        TF_CUDA(cudaMemcpy(block, A.data(), bytesA, cudaMemcpyHostToDevice));
+        TF_CUDA(cudaMemcpy((char*)block + bytesA, B.data(), bytesA, cudaMemcpyHostToDevice));
+        TF_CUDA(cudaMemcpy((char*)block + 2 * bytesA, obs64.data(), bytes64, cudaMemcpyHostToDevice));
+    }
+    env->dev_block = block;
+    EnvDev& d = env->d;
+    d.semantics = semantics;
+    d.n = n;
+    d.n_sphere = cnt[0]; d.n_cube = cnt[1]; d.n_cyl = cnt[2]; d.n_aabb = cnt[3];
+    d.tabA = (const float4*)block;
+    d.tabB = n > 0 ? (const float4*)((char*)block + bytesA) : nullptr;
+    d.obs64 = n > 0 ? (const double*)((char*)block + 2 * bytesA) : nullptr;
+    d.safety64 = safety;
+    return TF_OK;
+}
+
+static int env_create_common(int semantics, const std::vector<double>& obs64, int n, double safety, tf_env** out) {
+    if (!out) return TF_ERR_INVALID;
+    *out = nullptr;
+    if (semantics < TF_SEM_NONE || semantics > TF_SEM_PF || n < 0) return TF_ERR_INVALID;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    tf_env* env = (tf_env*)calloc(1, sizeof(tf_env));
+    if (!env) return TF_ERR_NOMEM;
+    if (semantics == TF_SEM_NONE) n = 0;
+    rc = upload_static(env, semantics, obs64, n, safety);
+    if (rc != TF_OK) { free(env); return rc; }
+    *out = env;
+    return TF_OK;
+}
+
+extern "C" int tf_env_create(int semantics, const tf_obstacle* obs_host, int n, float safety_radius, tf_env** out) {
+    if (n > 0 && !obs_host) return TF_ERR_INVALID;
+    std::vector<double> o64((size_t)(n > 0 ? n : 0) * 8);
+    for (int i = 0; i < n; ++i) {
+        const tf_obstacle& o = obs_host[i];
+        double* d = &o64[8 * (size_t)i];
+        d[0] = o.cx; d[1] = o.cy; d[2] = o.cz; d[3] = o.size; d[4] = o.hx; d[5] = o.hy; d[6] = o.hz; d[7] = (double)o.kind;
+    }
+    return env_create_common(semantics, o64, n, (double)safety_radius, out);
+}
+
+// f64 records: n x 8 doubles (cx cy cz size hx hy hz kind) — keeps positions/sizes that are not
+// representable in FP32 exact for the reference-order kernels.
+extern "C" int tf_env_create_f64(int semantics, const double* obs64_host, int n, double safety_radius, tf_env** out) {
+    if (n > 0 && !obs64_host) return TF_ERR_INVALID;
+    std::vector<double> o64(obs64_host, obs64_host + (size_t)(n > 0 ? n : 0) * 8);
+    return env_create_common(semantics, o64, n, safety_radius, out);
+}
+
+extern "C" int tf_env_set_dynamic(tf_env* env, const tf_dyn_obstacle* dyn_host, int n, float safety_radius) {
+    if (!env || n < 0 || (n > 0 && !dyn_host)) return TF_ERR_INVALID;
+    if (n > 2048) return TF_ERR_SHAPE;
+    if (env->dyn_block) { cudaFree(env->dyn_block); env->dyn_block = nullptr; }
+    env->d.n_dyn = 0; env->d.dynA = env->d.dynB = nullptr;
+    if (n == 0) return TF_OK;
+    std::vector<float> A((size_t)n * 4), B((size_t)n * 4);
+    for (int i = 0; i < n; ++i) {
+        const tf_dyn_obstacle& o = dyn_host[i];
+        float size = o.size < 0.0f ? 1.0f : o.size;
+        float r = size + safety_radius;
+        A[4 * i] = o.cx; A[4 * i + 1] = o.cy; A[4 * i + 2] = o.cz; A[4 * i + 3] = r * r;
+        B[4 * i] = o.vx; B[4 * i + 1] = o.vy; B[4 * i + 2] = o.vz; B[4 * i + 3] = 0.0f;
+    }
+    TF_CUDA(cudaMalloc(&env->dyn_block, (size_t)n * 32));
+    TF_CUDA(cudaMemcpy(env->dyn_block, A.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
+    TF_CUDA(cudaMemcpy((char*)env->dyn_block + (size_t)n * 16, B.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
+    env->d.n_dyn = n;
+    env->d.dynA = (const float4*)env->dyn_block;
+    env->d.dynB = (const float4*)((char*)env->dyn_block + (size_t)n * 16);
+    return TF_OK;
+}
+
+extern "C" int tf_env_set_voxels(tf_env* env, const uint32_t* bricks_dev, int nx, int ny, int nz) {
+    if (!env) return TF_ERR_INVALID;
+    if (!bricks_dev) { env->d.bricks = nullptr; return TF_OK; }
+    if (nx <= 0 || ny <= 0 || nz <= 0 || (nx & 7) || (ny & 7) || (nz & 7)) return TF_ERR_SHAPE;
+    env->d.bricks = bricks_dev;
+    env->d.nx = nx; env->d.ny = ny; env->d.nz = nz;
+    env->d.nbx = nx >> 3; env->d.nby = ny >> 3;
+    return TF_OK;
+}
+
+extern "C" int tf_env_set_hazard(tf_env* env, const float* hazard_dev, int nt, int ny, int nx, float sx, float sy,
+                                 float ox, float oy, float st) {
+    if (!env) return TF_ERR_INVALID;
+    if (!hazard_dev) { env->d.hazard = nullptr; return TF_OK; }
+    if (nt <= 0 || ny <= 0 || nx <= 0) return TF_ERR_SHAPE;
+    env->d.hazard = hazard_dev;
+    env->d.nt = nt; env->d.hny = ny; env->d.hnx = nx;
+    env->d.sx = sx; env->d.sy = sy; env->d.ox = ox; env->d.oy = oy; env->d.st = st;
+    return TF_OK;
+}
+
+extern "C" int tf_env_destroy(tf_env* env) {
+    if (!env) return TF_OK;
+    if (env->dev_block) cudaFree(env->dev_block);
+    if (env->dyn_block) cudaFree(env->dyn_block);
+    free(env);
+    return TF_OK;
+}
+
+// ------------------------------------------------------------------ voxel helpers
+extern "C" int64_t tf_voxel_grid_bytes(int nx, int ny, int nz) {
+    if (nx <= 0 || ny <= 0 || nz <= 0 || (nx & 7) || (ny & 7) || (nz & 7)) return TF_ERR_SHAPE;
+    return (int64_t)(nx >> 3) * (ny >> 3) * (nz >> 3) * 64;
+}
+
+extern "C" int tf_voxelize(int semantics, const tf_obstacle* obs_dev, int n, float safety_radius, uint32_t* bricks_dev,
+                           int nx, int ny, int nz, void* stream) {
+    if (!bricks_dev || (n > 0 && !obs_dev) || n < 0) return TF_ERR_INVALID;
+    if (semantics != TF_SEM_HR && semantics != TF_SEM_PF) return TF_ERR_INVALID;
+    if (tf_voxel_grid_bytes(nx, ny, nz) < 0) return TF_ERR_SHAPE;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    if (n == 0) return TF_OK;
+    const int threads = 256, warps_per_block = threads / 32;
+    voxelize_kernel<<<(n + warps_per_block - 1) / warps_per_block, threads, 0, (cudaStream_t)stream>>>(
+        semantics, obs_dev, n, safety_radius, bricks_dev, nx, ny, nz);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+
+extern "C" int tf_voxel_pack_linear(const uint32_t* linear_dev, uint32_t* bricks_dev, int nx, int ny, int nz,
+                                    void* stream) {
+    if (!linear_dev || !bricks_dev) return TF_ERR_INVALID;
+    int64_t bytes = tf_voxel_grid_bytes(nx, ny, nz);
+    if (bytes < 0) return TF_ERR_SHAPE;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    size_t nwords = (size_t)bytes / 4;
+    pack_linear_kernel<<<(unsigned)((nwords + 255) / 256), 256, 0, (cudaStream_t)stream>>>(linear_dev, bricks_dev, nx,
+                                                                                         ny, nz, nwords);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+
+// ------------------------------------------------------------------ misc
+extern "C" void tf_params_default(tf_params* p) {
+    if (!p) return;
+    p->w_safety = 0.4f; p->w_energy = 0.2f; p->w_wind = 0.2f; p->w_time = 0.1f; p->w_turn = 0.1f;  // HR:55-59
+    p->dist_zero_guard = 1;  // HR:53
+    p->hazard_weight = 0.0f;
+    p->samples_per_segment = 1;
+}
+
+extern "C" void tf_ga_params_default(tf_ga_params* p) {
+    if (!p) return;
+    p->n_elite = 2;  // HR:115
+    p->selection = TF_SEL_TRUNCATION;
+    p->n_top = 10;  // HR:118
+    p->tournament_k = 4;
+    p->crossover = TF_CX_SINGLE_POINT;
+    p->mutation = TF_MUT_LATTICE;
+    p->mutation_rate = 0.1f;  // HR:62
+    p->sigma = 1.0f;
+    p->stream_id = 0;
+    p->_pad = 0;
+}
+
+extern "C" int tf_version(void) { return TF_VERSION; }
+
+extern "C" const char* tf_strerror(int status) {
+    switch (status) {
+    case TF_OK: return "ok";
+    case TF_ERR_INVALID: return "invalid argument (null pointer or bad enum)";
+    case TF_ERR_SHAPE: return "shape out of supported range";
+    case TF_ERR_UNSUPPORTED: return "unsupported combination";
+    case TF_ERR_CUDA: return "CUDA runtime error (see tf_last_cuda_error)";
+    case TF_ERR_NOMEM: return "out of host memory";
+    case TF_ERR_NODEVICE: return "no sm_100 (B200) device: libtracefly_b200 has no fallback path";
+    case TF_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown tf_status";
+    }
+}
+
+extern "C" int tf_last_cuda_error(void) { return tf::g_last_cuda_error; }
+
+extern "C" int tf_device_info(int* sms, int* cc_major, int* cc_minor, int64_t* hbm_bytes) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return TF_ERR_NODEVICE;
+    }
+    if (sms) *sms = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (hbm_bytes) *hbm_bytes = (int64_t)prop.totalGlobalMem;
+    return TF_OK;
+}
+
+extern "C" void tf_philox4x32_10(uint32_t key0, uint32_t key1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                 uint32_t out[4]) {
+    tf::U4 r = tf::philox4x32_10(key0, key1, c0, c1, c2, c3);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+extern "C" int64_t tf_launch_count(void) { return (int64_t)tf::g_launch_count; }

@@ -1,0 +1,333 @@
+// tf_fitness_dev.cuh — device code of the FP32 fitness evaluation, one warp per chromosome.
+//
+// Replaces Path.calculate_fitness (HR:42-59 / PF:144-170) with is_collision (HR:17-23),
+// distance_to_nearest_obstacle (HR:25-28), ComplexEnvironment.is_obstacle (PF:28-44) and
+// distance_to_obstacles (PF:46-59).  The arithmetic order is the FP32 fixed-order model that
+// oracle/tf_oracle.c restates (orc_fitness_one_f32): lane l owns waypoints l, l+32, ...;
+// per-lane partial sums are accumulated in slot order and reduced with an xor butterfly.
+// Compiled with --fmad=false: every FMA below is explicit.
+#pragma once
+#include "tf_common.cuh"
+
+namespace tf {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kBlockThreads = kWarpsPerBlock * 32;
+constexpr int kTableCap = 2048;  // static obstacles staged per chunk (32 KB of float4)
+constexpr int kDynCap = 2048;
+
+struct Tables {  // shared-memory staging area handed to the evaluators
+    const float4* A;
+    const float4* B;
+    const float4* dA;
+    const float4* dB;
+};
+
+// One lane's slice of a chromosome: waypoint k = lane + 32*s lives in slot s.
+template <int NW>
+struct Lanes {
+    float x[NW], y[NW], z[NW];
+};
+
+__device__ __forceinline__ float dist2(float dx, float dy, float dz) {
+    return fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// Static analytic obstacles, table rows [lo, hi) of the staged chunk whose first row has global
+// index `base`.  Kind buckets are global index ranges (tables are kind-sorted).
+template <int SEM, int NP>
+__device__ __forceinline__ void eval_static_chunk(const EnvDev& e, const Tables& t, int base, int cnt,
+                                                  const float (&x)[NP], const float (&y)[NP], const float (&z)[NP],
+                                                  uint32_t& hit, float (&best)[NP]) {
+    if constexpr (SEM == TF_SEM_HR) {
+        // HR:17-28.  best[] carries min d^2 here; the caller takes one sqrt at the end.
+#pragma unroll 4
+        for (int k = 0; k < cnt; ++k) {
+            const float4 o = t.A[k];
+#pragma unroll
+            for (int s = 0; s < NP; ++s) {
+                float d2 = dist2(x[s] - o.x, y[s] - o.y, z[s] - o.z);
+                hit |= (d2 <= o.w) ? (1u << s) : 0u;
+                best[s] = fminf(best[s], d2);
+            }
+        }
+    } else if constexpr (SEM == TF_SEM_PF) {
+        const int s_end = e.n_sphere, c_end = s_end + e.n_cube, y_end = c_end + e.n_cyl;
+        int k = 0;
+        // spheres PF:37-39, PF:54-55
+        int lim = min(cnt, max(0, s_end - base));
+#pragma unroll 2
+        for (; k < lim; ++k) {
+            const float4 o = t.A[k];
+            const float s2 = __fmul_rn(o.w, o.w);
+#pragma unroll
+            for (int s = 0; s < NP; ++s) {
+                float d2 = dist2(x[s] - o.x, y[s] - o.y, z[s] - o.z);
+                hit |= (d2 <= s2) ? (1u << s) : 0u;
+                best[s] = fminf(best[s], fmaxf(0.0f, __fsub_rn(__fsqrt_rn(d2), o.w)));
+            }
+        }
+        // cubes PF:34-36 (Chebyshev collision), PF:52-53 (spherical distance)
+        lim = min(cnt, max(0, c_end - base));
+#pragma unroll 2
+        for (; k < lim; ++k) {
+            const float4 o = t.A[k];
+#pragma unroll
+            for (int s = 0; s < NP; ++s) {
+                float dx = x[s] - o.x, dy = y[s] - o.y, dz = z[s] - o.z;
+                bool in = fabsf(dx) <= o.w && fabsf(dy) <= o.w && fabsf(dz) <= o.w;
+                hit |= in ? (1u << s) : 0u;
+                best[s] = fminf(best[s], fmaxf(0.0f, __fsub_rn(__fsqrt_rn(dist2(dx, dy, dz)), o.w)));
+            }
+        }
+        // cylinders PF:40-42 (AABB s,s,2s), PF:56-57 (z-only distance)
+        lim = min(cnt, max(0, y_end - base));
+#pragma unroll 2
+        for (; k < lim; ++k) {
+            const float4 o = t.A[k];
+            const float h = __fmul_rn(2.0f, o.w);
+#pragma unroll
+            for (int s = 0; s < NP; ++s) {
+                float az = fabsf(z[s] - o.z);
+                bool in = fabsf(x[s] - o.x) <= o.w && fabsf(y[s] - o.y) <= o.w && az <= h;
+                hit |= in ? (1u << s) : 0u;
+                best[s] = fminf(best[s], fmaxf(0.0f, __fsub_rn(az, h)));
+            }
+        }
+        // AABBs (extension): true box distance
+        for (; k < cnt; ++k) {
+            const float4 o = t.A[k];
+            const float4 h = t.B[k];
+#pragma unroll
+            for (int s = 0; s < NP; ++s) {
+                float ax = fabsf(x[s] - o.x), ay = fabsf(y[s] - o.y), az = fabsf(z[s] - o.z);
+                bool in = ax <= h.x && ay <= h.y && az <= h.z;
+                hit |= in ? (1u << s) : 0u;
+                float qx = fmaxf(__fsub_rn(ax, h.x), 0.0f), qy = fmaxf(__fsub_rn(ay, h.y), 0.0f),
+                      qz = fmaxf(__fsub_rn(az, h.z), 0.0f);
+                best[s] = fminf(best[s], __fsqrt_rn(dist2(qx, qy, qz)));
+            }
+        }
+    }
+}
+
+// Moving spheres (extension): HR rules at c(t) = c0 + v t.  Returns min d^2 per point.
+template <int NP>
+__device__ __forceinline__ void eval_dynamic(const EnvDev& e, const Tables& t, const float (&x)[NP],
+                                             const float (&y)[NP], const float (&z)[NP], const float (&tm)[NP],
+                                             uint32_t& hit, float (&m2)[NP]) {
+    for (int k = 0; k < e.n_dyn; ++k) {
+        const float4 o = t.dA[k];
+        const float4 v = t.dB[k];
+#pragma unroll
+        for (int s = 0; s < NP; ++s) {
+            float cx = fmaf(v.x, tm[s], o.x), cy = fmaf(v.y, tm[s], o.y), cz = fmaf(v.z, tm[s], o.z);
+            float d2 = dist2(x[s] - cx, y[s] - cy, z[s] - cz);
+            hit |= (d2 <= o.w) ? (1u << s) : 0u;
+            m2[s] = fminf(m2[s], d2);
+        }
+    }
+}
+
+// Bit-packed occupancy probe through L2 (brick layout, include/tracefly_b200.h).
+__device__ __forceinline__ bool voxel_hit(const EnvDev& e, float x, float y, float z) {
+    int ix = __float2int_rd(x), iy = __float2int_rd(y), iz = __float2int_rd(z);
+    bool inb = (unsigned)ix < (unsigned)e.nx && (unsigned)iy < (unsigned)e.ny && (unsigned)iz < (unsigned)e.nz;
+    if (!inb) return false;
+    size_t brick = (size_t)(ix >> 3) + (size_t)e.nbx * ((size_t)(iy >> 3) + (size_t)e.nby * (size_t)(iz >> 3));
+    uint32_t w = __ldg(e.bricks + brick * 16 + ((iz & 7) * 2 + ((iy & 7) >> 2)));
+    return (w >> (((iy & 3) << 3) | (ix & 7))) & 1u;
+}
+
+__device__ __forceinline__ float lerp_f(float a, float b, float f) { return fmaf(f, __fsub_rn(b, a), a); }
+
+// Tri-linear hazard lookup (extension; the unused wind_data hook of PF:144).
+__device__ __forceinline__ float hazard_sample(const EnvDev& e, float x, float y, float t) {
+    float gx = fmaf(x, e.sx, e.ox), gy = fmaf(y, e.sy, e.oy), gt = __fmul_rn(t, e.st);
+    gx = fminf(fmaxf(gx, 0.0f), (float)(e.hnx - 1));
+    gy = fminf(fmaxf(gy, 0.0f), (float)(e.hny - 1));
+    gt = fminf(fmaxf(gt, 0.0f), (float)(e.nt - 1));
+    int x0 = (int)gx, y0 = (int)gy, t0 = (int)gt;
+    int x1 = min(x0 + 1, e.hnx - 1), y1 = min(y0 + 1, e.hny - 1), t1 = min(t0 + 1, e.nt - 1);
+    float fx = __fsub_rn(gx, (float)x0), fy = __fsub_rn(gy, (float)y0), ft = __fsub_rn(gt, (float)t0);
+    const float* h0 = e.hazard + (size_t)t0 * e.hny * e.hnx;
+    const float* h1 = e.hazard + (size_t)t1 * e.hny * e.hnx;
+    float v000 = __ldg(h0 + y0 * e.hnx + x0), v001 = __ldg(h0 + y0 * e.hnx + x1);
+    float v010 = __ldg(h0 + y1 * e.hnx + x0), v011 = __ldg(h0 + y1 * e.hnx + x1);
+    float v100 = __ldg(h1 + y0 * e.hnx + x0), v101 = __ldg(h1 + y0 * e.hnx + x1);
+    float v110 = __ldg(h1 + y1 * e.hnx + x0), v111 = __ldg(h1 + y1 * e.hnx + x1);
+    float a0 = lerp_f(lerp_f(v000, v001, fx), lerp_f(v010, v011, fx), fy);
+    float a1 = lerp_f(lerp_f(v100, v101, fx), lerp_f(v110, v111, fx), fy);
+    return lerp_f(a0, a1, ft);
+}
+
+// Full collision / nearest-distance evaluation of ONE point against a fully staged table
+// (sample points of the S > 1 extension; requires a single chunk).
+template <int SEM, bool VOX, bool EXTRA>
+__device__ __forceinline__ void eval_point_full(const EnvDev& e, const Tables& t, float x, float y, float z, float tm,
+                                                bool& hit_out, float& dnear) {
+    float xs[1] = {x}, ys[1] = {y}, zs[1] = {z}, tms[1] = {tm};
+    uint32_t hit = 0;
+    float best[1] = {INFINITY};
+    eval_static_chunk<SEM, 1>(e, t, 0, min(e.n, kTableCap), xs, ys, zs, hit, best);
+    float dn = (SEM == TF_SEM_HR) ? __fsqrt_rn(best[0]) : best[0];
+    if constexpr (EXTRA) {
+        if (e.n_dyn > 0) {
+            float m2[1] = {INFINITY};
+            eval_dynamic<1>(e, t, xs, ys, zs, tms, hit, m2);
+            dn = fminf(dn, __fsqrt_rn(m2[0]));
+        }
+    }
+    if constexpr (VOX) hit |= voxel_hit(e, x, y, z) ? 1u : 0u;
+    hit_out = hit != 0;
+    dnear = dn;
+}
+
+// Stage `cnt` table rows starting at global row `row0` into shared memory with the TMA engine.
+__device__ __forceinline__ void stage_chunk(const EnvDev& e, float4* sA, float4* sB, int row0, int cnt,
+                                            uint64_t* bar, bool with_dyn, float4* sdA, float4* sdB) {
+    // one elected thread arms the barrier with the byte count and issues the bulk copies
+    uint32_t bytes = (uint32_t)cnt * 16u * (e.n_aabb > 0 ? 2u : 1u);
+    if (with_dyn) bytes += (uint32_t)e.n_dyn * 32u;
+    mbar_expect_tx(bar, bytes);
+    if (cnt > 0) {
+        tma_load_1d(sA, e.tabA + row0, (uint32_t)cnt * 16u, bar);
+        if (e.n_aabb > 0) tma_load_1d(sB, e.tabB + row0, (uint32_t)cnt * 16u, bar);
+    }
+    if (with_dyn) {
+        tma_load_1d(sdA, e.dynA, (uint32_t)e.n_dyn * 16u, bar);
+        tma_load_1d(sdB, e.dynB, (uint32_t)e.n_dyn * 16u, bar);
+    }
+}
+
+struct SmemLayout {
+    uint64_t* bar;
+    float4 *A, *B, *dA, *dB;
+};
+__host__ __device__ inline size_t smem_bytes_for(const EnvDev& e) {
+    size_t cap = (size_t)(e.n < kTableCap ? e.n : kTableCap);
+    return 16 + cap * 16 * (e.n_aabb > 0 ? 2 : 1) + (size_t)e.n_dyn * 32;
+}
+__device__ __forceinline__ SmemLayout carve_smem(const EnvDev& e, unsigned char* smem) {
+    SmemLayout s;
+    size_t cap = (size_t)min(e.n, kTableCap);
+    s.bar = reinterpret_cast<uint64_t*>(smem);
+    s.A = reinterpret_cast<float4*>(smem + 16);
+    s.B = s.A + (e.n_aabb > 0 ? cap : 0);
+    s.dA = s.B + cap;
+    if (e.n_aabb == 0) s.dA = s.A + cap;
+    s.dB = s.dA + e.n_dyn;
+    return s;
+}
+
+// Per-warp evaluation state shared by tf_fitness and the fused tf_generation kernel.
+//   cur      : this lane's waypoints (slot s = waypoint lane + 32 s), already in registers
+//   L        : valid waypoint count of the chromosome
+// The CTA-uniform chunk loop lives in the caller when the table needs more than one chunk;
+// this struct holds the accumulators across chunks.
+template <int NW, int SEM>
+struct PointAcc {
+    uint32_t hit;
+    float best[NW];
+    __device__ __forceinline__ void reset() {
+        hit = 0;
+#pragma unroll
+        for (int s = 0; s < NW; ++s) best[s] = INFINITY;
+    }
+};
+
+// Finish a chromosome once the static-obstacle accumulators are complete.  Returns the fitness
+// (valid in every lane) and writes collision words through `coll_row` (may be NULL).
+template <int NW, int SEM, bool VOX, bool EXTRA>
+__device__ __forceinline__ float finish_chromosome(const EnvDev& e, const tf_params& prm, const Tables& t,
+                                                   const Lanes<NW>& cur, int L, PointAcc<NW, SEM>& acc,
+                                                   uint32_t* coll_row, int nwords) {
+    const int lane = threadIdx.x & 31;
+    float a_prox = 0.0f, a_dist = 0.0f, a_alt = 0.0f, a_haz = 0.0f;
+    int turns = 0, ncoll = 0;
+    uint32_t hit = acc.hit;
+    float dn[NW];
+#pragma unroll
+    for (int s = 0; s < NW; ++s) dn[s] = (SEM == TF_SEM_HR) ? __fsqrt_rn(acc.best[s]) : acc.best[s];
+    if constexpr (EXTRA) {
+        if (e.n_dyn > 0) {
+            float m2[NW], tm[NW];
+#pragma unroll
+            for (int s = 0; s < NW; ++s) {
+                m2[s] = INFINITY;
+                tm[s] = (float)(lane + 32 * s);
+            }
+            eval_dynamic<NW>(e, t, cur.x, cur.y, cur.z, tm, hit, m2);
+#pragma unroll
+            for (int s = 0; s < NW; ++s) dn[s] = fminf(dn[s], __fsqrt_rn(m2[s]));
+        }
+    }
+    const int S = EXTRA ? max(prm.samples_per_segment, 1) : 1;
+    // previous waypoint of each slot: rotate by one lane; lane 0 takes lane 31 of the previous slot
+    float rx_prev = 0.f, ry_prev = 0.f, rz_prev = 0.f;
+#pragma unroll
+    for (int s = 0; s < NW; ++s) {
+        const int k = lane + 32 * s;
+        const bool valid = k < L;
+        const int src = (lane + 31) & 31;
+        float rx = __shfl_sync(0xffffffffu, cur.x[s], src);
+        float ry = __shfl_sync(0xffffffffu, cur.y[s], src);
+        float rz = __shfl_sync(0xffffffffu, cur.z[s], src);
+        float px = lane == 0 ? rx_prev : rx, py = lane == 0 ? ry_prev : ry, pz = lane == 0 ? rz_prev : rz;
+        rx_prev = rx; ry_prev = ry; rz_prev = rz;
+        bool h = (hit >> s) & 1u;
+        if constexpr (VOX) h = h || voxel_hit(e, cur.x[s], cur.y[s], cur.z[s]);
+        h = h && valid;
+        if (coll_row != nullptr) {
+            uint32_t word = __ballot_sync(0xffffffffu, h);
+            if (lane == 0 && s < nwords) coll_row[s] = word;
+        }
+        if (valid) {
+            ncoll += h ? 1 : 0;
+            a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[s])));  // HR:46
+            if constexpr (EXTRA) {
+                if (e.hazard != nullptr) a_haz = __fadd_rn(a_haz, hazard_sample(e, cur.x[s], cur.y[s], (float)k));
+            }
+            if (k >= 1) {
+                float dx = cur.x[s] - px, dy = cur.y[s] - py, dz = cur.z[s] - pz;
+                a_dist = __fadd_rn(a_dist, __fsqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
+                a_alt = __fadd_rn(a_alt, fabsf(dz));                         // HR:44
+                if (k <= L - 2) turns += (cur.x[s] != px || cur.y[s] != py) ? 1 : 0;  // HR:38-40,43
+                if constexpr (EXTRA) {
+                    for (int j = 1; j < S; ++j) {  // extension: samples inside segment (k-1, k)
+                        float tj = __fdiv_rn((float)j, (float)S);
+                        bool sh;
+                        float sdn;
+                        eval_point_full<SEM, VOX, EXTRA>(e, t, fmaf(dx, tj, px), fmaf(dy, tj, py), fmaf(dz, tj, pz),
+                                                         __fadd_rn((float)(k - 1), tj), sh, sdn);
+                        ncoll += sh ? 1 : 0;
+                        a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, sdn)));
+                    }
+                }
+            }
+        }
+    }
+    const float prox = warp_sum_xor(a_prox), dist = warp_sum_xor(a_dist), alt = warp_sum_xor(a_alt);
+    const int packed = __reduce_add_sync(0xffffffffu, turns | (ncoll << 10));
+    turns = packed & 1023;
+    ncoll = packed >> 10;
+    const float tf_ = (float)turns;
+    const float pen = __fadd_rn((float)ncoll, prox);                         // HR:45-46
+    const float safety = __fdiv_rn(1.0f, __fadd_rn(1.0f, pen));              // HR:47
+    const float energy = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(1.0f, tf_), alt));  // HR:48
+    float windden = __fadd_rn(1.0f, alt);                                    // HR:49
+    if constexpr (EXTRA) {
+        if (e.hazard != nullptr) windden = fmaf(prm.hazard_weight, warp_sum_xor(a_haz), windden);
+    }
+    const float wind = __fdiv_rn(1.0f, windden);
+    const float time_s = (dist != 0.0f) ? __fdiv_rn(1.0f, dist) : (prm.dist_zero_guard ? 0.0f : INFINITY);  // HR:53 / PF:163
+    const float ts = __fdiv_rn(1.0f, __fadd_rn(1.0f, tf_));
+    float f = __fmul_rn(prm.w_safety, safety);                               // HR:55-59
+    f = fmaf(prm.w_energy, energy, f);
+    f = fmaf(prm.w_wind, wind, f);
+    f = fmaf(prm.w_time, time_s, f);
+    f = fmaf(prm.w_turn, ts, f);
+    return f;
+}
+
+}  // namespace tf
