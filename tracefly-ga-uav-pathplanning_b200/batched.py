@@ -185,6 +185,8 @@ def fitness_batch(pop, lens, env, params=None, out=None, want_collisions=True):
     params = params or L.default_params(dist_zero_guard=1 if env.semantics != L.SEM_PF else 0)
     fit = out if out is not None else torch.empty(P, dtype=torch.float32, device=pop.device)
     coll = torch.empty((P, (W + 31) // 32), dtype=torch.int32, device=pop.device) if want_collisions else None
+    if P == 0:
+        return fit, coll
     check(lib.tf_fitness(env.handle, _ptr(pop), _ptr(lens), P, W, C.byref(params), _ptr(fit), _ptr(coll), _stream()),
           "tf_fitness")
     return fit, coll

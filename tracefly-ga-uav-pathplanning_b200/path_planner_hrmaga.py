@@ -227,7 +227,7 @@ def generate_local_path(start_point, end_point, planner=None):
             "path": best_path,
             "start": start_point,
             "end": end_point,
-            "timestamp": datetime.utcnow().isoformat(),
+            "timestamp": datetime.utcnow().isoformat()  # noqa: same call as HR:152,
         }
         with open(output_file, "w") as f:
             json.dump(output_data, f, indent=2)
