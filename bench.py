@@ -90,43 +90,45 @@ def algorithmic_bytes_per_unit(W, fused=True):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (profiling recipe)."""
+    """SM clock + throttle reasons sampled DURING the timed region through NVML (the same counters
+    nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.* prints), every 5 ms."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
+        self.index, self.sm, self.reasons, self.power = index, [], set(), []
         self.stop_flag = False
-        self.proc = None
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def run(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                self.samples.append([x.strip() for x in line.split(",")])
-        except Exception:
-            pass
+        while not self.stop_flag and self.nv is not None:
+            try:
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def finish(self):
         self.stop_flag = True
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            for n, v in zip(names, s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.join(timeout=1.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None}
 
 
 def measured_peak_gbs():
@@ -202,12 +204,11 @@ def run_gpu(args):
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream, max over ranks
     sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.25)
     gen_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = L.launch_count()
     sync_all()
+    sampler.start()
     t0.record(stream)
     for i in range(args.steps):
         # the per-step events bracket ONLY the dominant kernel (tf_generation) for the roofline
@@ -394,7 +395,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))

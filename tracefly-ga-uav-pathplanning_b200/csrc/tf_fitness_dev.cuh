@@ -236,16 +236,46 @@ struct PointAcc {
     }
 };
 
-// Finish a chromosome once the static-obstacle accumulators are complete.  Returns the fitness
-// (valid in every lane) and writes collision words through `coll_row` (may be NULL).
+// ---- tile structure -----------------------------------------------------------------------
+// A warp works on a TILE of 32 chromosomes.  Phase B (lane = waypoint) walks the tile one
+// chromosome at a time and leaves that chromosome's warp-reduced sums in lane c of a TileSums;
+// phase C (lane = chromosome) then does the final score arithmetic (5 IEEE divisions) for all 32
+// at once and writes fitness / collision words coalesced.  Per-chromosome scalar work is thereby
+// paid once per 32 chromosomes instead of once per warp (ncu round 1: 842 warp-instr/chromosome
+// when every lane redundantly did the scalar work).
+template <int NW>
+struct TileSums {
+    float prox, dist, alt, haz;
+    int packed;            // turns | ncoll << 10
+    uint32_t cw[NW];       // collision words
+    __device__ __forceinline__ void reset() {
+        prox = dist = alt = haz = 0.0f;
+        packed = 0;
+#pragma unroll
+        for (int s = 0; s < NW; ++s) cw[s] = 0;
+    }
+};
+
+// Chromosomes per warp tile: 32 when the population fills the machine, fewer for small P so
+// that there are still enough tiles to occupy every SM (lanes >= T idle in phases A / C).
+inline int tile_size_for(int P) {
+    const long long target_warps = (long long)sm_count() * 48;
+    int T = 32;
+    while (T > 4 && (long long)P / T < target_warps) T >>= 1;
+    return T;
+}
+
+// Phase B for one chromosome (all 32 lanes cooperate; `c` = its index in the tile).
 template <int NW, int SEM, bool VOX, bool EXTRA>
-__device__ __forceinline__ float finish_chromosome(const EnvDev& e, const tf_params& prm, const Tables& t,
-                                                   const Lanes<NW>& cur, int L, PointAcc<NW, SEM>& acc,
-                                                   uint32_t* coll_row, int nwords) {
+__device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_params& prm, const Tables& t,
+                                                  const Lanes<NW>& cur, int L, PointAcc<NW, SEM>& acc, int c,
+                                                  TileSums<NW>& out) {
     const int lane = threadIdx.x & 31;
     float a_prox = 0.0f, a_dist = 0.0f, a_alt = 0.0f, a_haz = 0.0f;
     int turns = 0, ncoll = 0;
     uint32_t hit = acc.hit;
+    // without any distance source d_near = inf and every proximity term is exactly 0 (HR:26-27)
+    const bool has_dist = (SEM != TF_SEM_NONE) || (EXTRA && e.n_dyn > 0);
     float dn[NW];
 #pragma unroll
     for (int s = 0; s < NW; ++s) dn[s] = (SEM == TF_SEM_HR) ? __fsqrt_rn(acc.best[s]) : acc.best[s];
@@ -278,49 +308,59 @@ __device__ __forceinline__ float finish_chromosome(const EnvDev& e, const tf_par
         bool h = (hit >> s) & 1u;
         if constexpr (VOX) h = h || voxel_hit(e, cur.x[s], cur.y[s], cur.z[s]);
         h = h && valid;
-        if (coll_row != nullptr) {
-            uint32_t word = __ballot_sync(0xffffffffu, h);
-            if (lane == 0 && s < nwords) coll_row[s] = word;
+        const uint32_t word = __ballot_sync(0xffffffffu, h);
+        if (lane == c) out.cw[s] = word;
+        ncoll += h ? 1 : 0;
+        if (has_dist && valid) a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[s])));  // HR:46
+        if constexpr (EXTRA) {
+            if (e.hazard != nullptr && valid) a_haz = __fadd_rn(a_haz, hazard_sample(e, cur.x[s], cur.y[s], (float)k));
         }
-        if (valid) {
-            ncoll += h ? 1 : 0;
-            a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[s])));  // HR:46
+        if (valid && k >= 1) {
+            float dx = cur.x[s] - px, dy = cur.y[s] - py, dz = cur.z[s] - pz;
+            a_dist = __fadd_rn(a_dist, __fsqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
+            a_alt = __fadd_rn(a_alt, fabsf(dz));                         // HR:44
+            if (k <= L - 2) turns += (cur.x[s] != px || cur.y[s] != py) ? 1 : 0;  // HR:38-40,43
             if constexpr (EXTRA) {
-                if (e.hazard != nullptr) a_haz = __fadd_rn(a_haz, hazard_sample(e, cur.x[s], cur.y[s], (float)k));
-            }
-            if (k >= 1) {
-                float dx = cur.x[s] - px, dy = cur.y[s] - py, dz = cur.z[s] - pz;
-                a_dist = __fadd_rn(a_dist, __fsqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
-                a_alt = __fadd_rn(a_alt, fabsf(dz));                         // HR:44
-                if (k <= L - 2) turns += (cur.x[s] != px || cur.y[s] != py) ? 1 : 0;  // HR:38-40,43
-                if constexpr (EXTRA) {
-                    for (int j = 1; j < S; ++j) {  // extension: samples inside segment (k-1, k)
-                        float tj = __fdiv_rn((float)j, (float)S);
-                        bool sh;
-                        float sdn;
-                        eval_point_full<SEM, VOX, EXTRA>(e, t, fmaf(dx, tj, px), fmaf(dy, tj, py), fmaf(dz, tj, pz),
-                                                         __fadd_rn((float)(k - 1), tj), sh, sdn);
-                        ncoll += sh ? 1 : 0;
-                        a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, sdn)));
-                    }
+                for (int j = 1; j < S; ++j) {  // extension: samples inside segment (k-1, k)
+                    float tj = __fdiv_rn((float)j, (float)S);
+                    bool sh;
+                    float sdn;
+                    eval_point_full<SEM, VOX, EXTRA>(e, t, fmaf(dx, tj, px), fmaf(dy, tj, py), fmaf(dz, tj, pz),
+                                                     __fadd_rn((float)(k - 1), tj), sh, sdn);
+                    ncoll += sh ? 1 : 0;
+                    if (has_dist) a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, sdn)));
                 }
             }
         }
     }
-    const float prox = warp_sum_xor(a_prox), dist = warp_sum_xor(a_dist), alt = warp_sum_xor(a_alt);
+    const float dist = warp_sum_xor(a_dist), alt = warp_sum_xor(a_alt);
     const int packed = __reduce_add_sync(0xffffffffu, turns | (ncoll << 10));
-    turns = packed & 1023;
-    ncoll = packed >> 10;
-    const float tf_ = (float)turns;
-    const float pen = __fadd_rn((float)ncoll, prox);                         // HR:45-46
-    const float safety = __fdiv_rn(1.0f, __fadd_rn(1.0f, pen));              // HR:47
-    const float energy = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(1.0f, tf_), alt));  // HR:48
-    float windden = __fadd_rn(1.0f, alt);                                    // HR:49
+    if (lane == c) { out.dist = dist; out.alt = alt; out.packed = packed; }
+    if (has_dist) {
+        const float prox = warp_sum_xor(a_prox);
+        if (lane == c) out.prox = prox;
+    }
     if constexpr (EXTRA) {
-        if (e.hazard != nullptr) windden = fmaf(prm.hazard_weight, warp_sum_xor(a_haz), windden);
+        if (e.hazard != nullptr) {
+            const float haz = warp_sum_xor(a_haz);
+            if (lane == c) out.haz = haz;
+        }
+    }
+}
+
+// Phase C: the score arithmetic of HR:45-59 for this lane's chromosome.
+template <int NW, bool EXTRA>
+__device__ __forceinline__ float combine_fitness(const EnvDev& e, const tf_params& prm, const TileSums<NW>& s) {
+    const float tf_ = (float)(s.packed & 1023);
+    const float pen = __fadd_rn((float)(s.packed >> 10), s.prox);            // HR:45-46
+    const float safety = __fdiv_rn(1.0f, __fadd_rn(1.0f, pen));              // HR:47
+    const float energy = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(1.0f, tf_), s.alt));  // HR:48
+    float windden = __fadd_rn(1.0f, s.alt);                                  // HR:49
+    if constexpr (EXTRA) {
+        if (e.hazard != nullptr) windden = fmaf(prm.hazard_weight, s.haz, windden);
     }
     const float wind = __fdiv_rn(1.0f, windden);
-    const float time_s = (dist != 0.0f) ? __fdiv_rn(1.0f, dist) : (prm.dist_zero_guard ? 0.0f : INFINITY);  // HR:53 / PF:163
+    const float time_s = (s.dist != 0.0f) ? __fdiv_rn(1.0f, s.dist) : (prm.dist_zero_guard ? 0.0f : INFINITY);  // HR:53 / PF:163
     const float ts = __fdiv_rn(1.0f, __fadd_rn(1.0f, tf_));
     float f = __fmul_rn(prm.w_safety, safety);                               // HR:55-59
     f = fmaf(prm.w_energy, energy, f);

@@ -10,41 +10,89 @@
 namespace tf {
 
 // ------------------------------------------------------------------------------------------
-// Unfused GA step: one warp per slot of the next population.  V4 = float4 / double4.
+// Phase-B plan broadcast: everything the 32 lanes need to move child c's waypoints.
+template <int NW>
+struct PlanB {
+    int first, second, cp, mp, L;
+    float dx, dy, dz;
+    uint32_t mask[NW];
+};
+template <int NW>
+__device__ __forceinline__ PlanB<NW> broadcast_plan(const ChildPlan<NW>& mine, int c, bool uniform) {
+    PlanB<NW> b;
+    b.first = __shfl_sync(0xffffffffu, mine.first, c);
+    b.second = __shfl_sync(0xffffffffu, mine.second, c);
+    const int meta = __shfl_sync(0xffffffffu, mine.meta, c);
+    b.cp = meta_cp(meta);
+    b.mp = meta_mp(meta);
+    b.L = meta_len(meta);
+    b.dx = b.dy = b.dz = 0.0f;
+    if (b.mp >= 0) {  // warp-uniform
+        b.dx = __shfl_sync(0xffffffffu, mine.dx, c);
+        b.dy = __shfl_sync(0xffffffffu, mine.dy, c);
+        b.dz = __shfl_sync(0xffffffffu, mine.dz, c);
+    }
+#pragma unroll
+    for (int s = 0; s < NW; ++s) b.mask[s] = uniform ? __shfl_sync(0xffffffffu, mine.mask[s], c) : 0u;
+    return b;
+}
+template <int NW>
+__device__ __forceinline__ bool from_first(const PlanB<NW>& b, int k, int s, int lane) {
+    return (k < b.cp) && !((b.mask[s] >> lane) & 1u);  // HR:87-88; uniform: cp = 511 and the mask decides
+}
+
+// Phase A for a tile: this lane's slot.
+template <int NW, typename F>
+__device__ __forceinline__ ChildPlan<NW> plan_slot(int slot, int ne, const F* fit, const int32_t* lens,
+                                                  const int32_t* top_idx, const tf_draw* tape, uint64_t seed,
+                                                  uint32_t gen, const tf_ga_params& ga, int P, int W,
+                                                  int32_t* sel, int32_t* cpo) {
+    if (slot >= P) return plan_elite<NW>(0, 0);
+    if (slot < ne) {  // HR:115 elitism
+        const int src = top_idx[slot];
+        return plan_elite<NW>(src, lens ? lens[src] : W);
+    }
+    ChildPlan<NW> pl = plan_child<NW, F>(slot, ne, fit, lens, top_idx, tape, seed, gen, ga, P, W);
+    if (((slot - ne) & 1) == 0) {
+        const int j = (slot - ne) >> 1;
+        if (sel) { sel[2 * j] = pl.ia; sel[2 * j + 1] = pl.ib; }
+        if (cpo) cpo[j] = (ga.crossover == TF_CX_UNIFORM && tape == nullptr) ? 0 : meta_cp(pl.meta);
+    }
+    return pl;
+}
+
+// Unfused GA step: one warp per tile of 32 slots.  V4 = float4 / double4.  (W <= 256: NW = 8.)
 template <typename V4, typename F>
 __global__ void __launch_bounds__(kBlockThreads)
 ga_step_kernel(const V4* __restrict__ pop, const int32_t* __restrict__ lens, const F* __restrict__ fit,
                const int32_t* __restrict__ top_idx, const tf_draw* __restrict__ tape, uint64_t seed, uint32_t gen,
-               const __grid_constant__ tf_ga_params ga, int P, int W, V4* __restrict__ next,
+               const __grid_constant__ tf_ga_params ga, int P, int W, int T, V4* __restrict__ next,
                int32_t* __restrict__ next_lens, int32_t* __restrict__ sel, int32_t* __restrict__ cpo) {
+    constexpr int NW = 8;
     const int lane = threadIdx.x & 31;
     const int ne = min(ga.n_elite, P);
-    for (int slot = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); slot < P; slot += gridDim.x * kWarpsPerBlock) {
-        V4* dst = next + (size_t)slot * W;
-        if (slot < ne) {  // HR:115 elitism
-            const int src = top_idx[slot];
-            for (int k = lane; k < W; k += 32) dst[k] = pop[(size_t)src * W + k];
-            if (next_lens && lane == 0) next_lens[slot] = lens ? lens[src] : W;
-            continue;
-        }
-        const int j = (slot - ne) >> 1, c = (slot - ne) & 1;
-        const ChildPlan pl = plan_child<F>(j, c, fit, lens, top_idx, tape, seed, gen, ga, P, W);
-        if (c == 0 && lane == 0) {
-            if (sel) { sel[2 * j] = pl.ia; sel[2 * j + 1] = pl.ib; }
-            if (cpo) cpo[j] = pl.cp;
-        }
-        const V4* ra = pop + (size_t)pl.first * W;
-        const V4* rb = pop + (size_t)pl.second * W;
-        for (int k = lane, s = 0; k < W; k += 32, ++s) {
-            V4 v = from_first(pl, k, s) ? ra[k] : rb[k];
-            if (k == pl.mp) {  // HR:97-98
-                v.x = v.x + (decltype(v.x))pl.dx;
-                v.y = v.y + (decltype(v.y))pl.dy;
-                v.z = v.z + (decltype(v.z))pl.dz;
+    const bool uniform = ga.crossover == TF_CX_UNIFORM && tape == nullptr;
+    const int ntiles = (P + T - 1) / T;
+    for (int tile = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); tile < ntiles; tile += gridDim.x * kWarpsPerBlock) {
+        const int slot0 = tile * T;
+        const int cnt = min(T, P - slot0);
+        const ChildPlan<NW> mine = plan_slot<NW, F>(lane < T ? slot0 + lane : P, ne, fit, lens, top_idx, tape, seed, gen, ga, P, W, sel, cpo);
+        if (next_lens && lane < cnt) next_lens[slot0 + lane] = meta_len(mine.meta);
+        for (int c = 0; c < cnt; ++c) {
+            const PlanB<NW> b = broadcast_plan<NW>(mine, c, uniform);
+            const V4* ra = pop + (size_t)b.first * W;
+            const V4* rb = pop + (size_t)b.second * W;
+            V4* dst = next + (size_t)(slot0 + c) * W;
+            for (int k = lane, s = 0; k < W; k += 32, ++s) {
+                V4 v = from_first<NW>(b, k, s, lane) ? ra[k] : rb[k];
+                if (k == b.mp) {  // HR:97-98
+                    v.x = v.x + (decltype(v.x))b.dx;
+                    v.y = v.y + (decltype(v.y))b.dy;
+                    v.z = v.z + (decltype(v.z))b.dz;
+                }
+                dst[k] = v;
             }
-            dst[k] = v;
         }
-        if (next_lens && lane == 0) next_lens[slot] = pl.L;
     }
 }
 
@@ -60,10 +108,12 @@ static int run_ga_step(const S* pop, const int32_t* lens, const F* fit, const in
     if (lens && ga->crossover == TF_CX_UNIFORM) return TF_ERR_UNSUPPORTED;  // uniform crossover needs fixed W
     int rc = ensure_device();
     if (rc != TF_OK) return rc;
-    int grid = min((P + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
+    const int T = tile_size_for(P);
+    const int ntiles = (P + T - 1) / T;
+    int grid = min((ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
     ga_step_kernel<V4, F><<<grid, kBlockThreads, 0, st>>>(reinterpret_cast<const V4*>(pop), lens, fit, top_idx, tape,
-                                                         seed, gen, *ga, P, W, reinterpret_cast<V4*>(next), next_lens,
-                                                         sel, cpo);
+                                                         seed, gen, *ga, P, W, T, reinterpret_cast<V4*>(next),
+                                                         next_lens, sel, cpo);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
@@ -71,12 +121,15 @@ static int run_ga_step(const S* pop, const int32_t* lens, const F* fit, const in
 // ------------------------------------------------------------------------------------------
 // Fused generation: child built in registers -> streamed to next_pop -> evaluated by the same
 // warp.  Same results as tf_ga_step followed by tf_fitness (fixed W, single table chunk).
+// Tile structure: phase A (lane = slot) plans 32 children; phase B (lane = waypoint) builds,
+// stores and reduces one child at a time with the next child's parents already in flight;
+// phase C (lane = slot) scores the 32 children and writes fitness / flags coalesced.
 template <int NW, int SEM, bool VOX, bool EXTRA>
 __global__ void __launch_bounds__(kBlockThreads)
 generation_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
                   const __grid_constant__ tf_ga_params ga, const float4* __restrict__ pop,
                   const float* __restrict__ fit, const int32_t* __restrict__ top_idx,
-                  const tf_draw* __restrict__ tape, uint64_t seed, uint32_t gen, int P, int W,
+                  const tf_draw* __restrict__ tape, uint64_t seed, uint32_t gen, int P, int W, int T,
                   float4* __restrict__ next, float* __restrict__ next_fit, uint32_t* __restrict__ next_coll,
                   int32_t* __restrict__ sel, int32_t* __restrict__ cpo) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -85,6 +138,7 @@ generation_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_p
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwords = (W + 31) >> 5;
     const int ne = min(ga.n_elite, P);
+    const bool uniform = ga.crossover == TF_CX_UNIFORM && tape == nullptr;
     if ((SEM != TF_SEM_NONE && e.n > 0) || (EXTRA && e.n_dyn > 0)) {
         if (threadIdx.x == 0) {
             mbar_init(sm.bar, 1);
@@ -95,49 +149,65 @@ generation_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_p
             stage_chunk(e, sm.A, sm.B, 0, min(e.n, kTableCap), sm.bar, EXTRA && e.n_dyn > 0, sm.dA, sm.dB);
         mbar_wait(sm.bar, 0);
     }
-    for (int slot = blockIdx.x * kWarpsPerBlock + warp; slot < P; slot += gridDim.x * kWarpsPerBlock) {
-        Lanes<NW> cur;
-        float4* dst = next + (size_t)slot * W;
-        if (slot < ne) {  // HR:115 elites are carried over and re-evaluated (HR:123-124)
-            const float4* src = pop + (size_t)top_idx[slot] * W;
-#pragma unroll
-            for (int s = 0; s < NW; ++s) {
-                const int k = lane + 32 * s;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k < W) { v = src[k]; stg_stream(dst + k, v); }
-                cur.x[s] = v.x; cur.y[s] = v.y; cur.z[s] = v.z;
-            }
-        } else {
-            const int j = (slot - ne) >> 1, c = (slot - ne) & 1;
-            const ChildPlan pl = plan_child<float>(j, c, fit, nullptr, top_idx, tape, seed, gen, ga, P, W);
-            if (c == 0 && lane == 0) {
-                if (sel) { sel[2 * j] = pl.ia; sel[2 * j + 1] = pl.ib; }
-                if (cpo) cpo[j] = pl.cp;
-            }
-            const float4* ra = pop + (size_t)pl.first * W;
-            const float4* rb = pop + (size_t)pl.second * W;
+    const int ntiles = (P + T - 1) / T;
+    for (int tile = blockIdx.x * kWarpsPerBlock + warp; tile < ntiles; tile += gridDim.x * kWarpsPerBlock) {
+        const int slot0 = tile * T;
+        const int cnt = min(T, P - slot0);
+        // phase A
+        const ChildPlan<NW> mine = plan_slot<NW, float>(lane < T ? slot0 + lane : P, ne, fit, nullptr, top_idx, tape, seed, gen, ga, P, W, sel, cpo);
+        TileSums<NW> sums;
+        sums.reset();
+
+        auto fetch = [&](int c, Lanes<NW>& dst, float (&w4)[NW]) {  // gather + mutate child c into registers
+            const PlanB<NW> b = broadcast_plan<NW>(mine, c, uniform);
+            const float4* ra = pop + (size_t)b.first * W;
+            const float4* rb = pop + (size_t)b.second * W;
 #pragma unroll
             for (int s = 0; s < NW; ++s) {
                 const int k = lane + 32 * s;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (k < W) {
-                    v = ldg_stream(from_first(pl, k, s) ? ra + k : rb + k);
-                    if (k == pl.mp) {  // HR:97-98
-                        v.x = __fadd_rn(v.x, pl.dx);
-                        v.y = __fadd_rn(v.y, pl.dy);
-                        v.z = __fadd_rn(v.z, pl.dz);
+                    v = ldg_stream(from_first<NW>(b, k, s, lane) ? ra + k : rb + k);
+                    if (k == b.mp) {  // HR:97-98
+                        v.x = __fadd_rn(v.x, b.dx);
+                        v.y = __fadd_rn(v.y, b.dy);
+                        v.z = __fadd_rn(v.z, b.dz);
                     }
-                    stg_stream(dst + k, v);
                 }
-                cur.x[s] = v.x; cur.y[s] = v.y; cur.z[s] = v.z;
+                dst.x[s] = v.x; dst.y[s] = v.y; dst.z[s] = v.z; w4[s] = v.w;
+            }
+        };
+
+        Lanes<NW> cur, nxt;
+        float cw4[NW], nw4[NW];
+        fetch(0, cur, cw4);
+#pragma unroll 1
+        for (int c = 0; c < cnt; ++c) {
+            if (c + 1 < cnt) fetch(c + 1, nxt, nw4);
+            float4* dst = next + (size_t)(slot0 + c) * W;
+#pragma unroll
+            for (int s = 0; s < NW; ++s) {
+                const int k = lane + 32 * s;
+                if (k < W) stg_stream(dst + k, make_float4(cur.x[s], cur.y[s], cur.z[s], cw4[s]));
+            }
+            PointAcc<NW, SEM> acc;
+            acc.reset();
+            if constexpr (SEM != TF_SEM_NONE) eval_static_chunk<SEM, NW>(e, tabs, 0, e.n, cur.x, cur.y, cur.z, acc.hit, acc.best);
+            reduce_chromosome<NW, SEM, VOX, EXTRA>(e, prm, tabs, cur, W, acc, c, sums);
+            cur = nxt;
+#pragma unroll
+            for (int s = 0; s < NW; ++s) cw4[s] = nw4[s];
+        }
+        // phase C
+        if (lane < cnt) {
+            const int slot = slot0 + lane;
+            next_fit[slot] = combine_fitness<NW, EXTRA>(e, prm, sums);
+            if (next_coll) {
+#pragma unroll
+                for (int s = 0; s < NW; ++s)
+                    if (s < nwords) next_coll[(size_t)slot * nwords + s] = sums.cw[s];
             }
         }
-        PointAcc<NW, SEM> acc;
-        acc.reset();
-        if constexpr (SEM != TF_SEM_NONE) eval_static_chunk<SEM, NW>(e, tabs, 0, e.n, cur.x, cur.y, cur.z, acc.hit, acc.best);
-        const float f = finish_chromosome<NW, SEM, VOX, EXTRA>(e, prm, tabs, cur, W, acc,
-                                                               next_coll ? next_coll + (size_t)slot * nwords : nullptr, nwords);
-        if (lane == 0) next_fit[slot] = f;
     }
 }
 
@@ -152,9 +222,11 @@ static int launch_generation(const GenArgs& a) {
     auto kern = generation_kernel<NW, SEM, VOX, EXTRA>;
     size_t smem = smem_bytes_for(*a.e);
     if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = min((a.P + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
+    const int T = tile_size_for(a.P);
+    const int ntiles = (a.P + T - 1) / T;
+    int grid = min((ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
     kern<<<grid, kBlockThreads, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
-                                              a.top_idx, a.tape, a.seed, a.gen, a.P, a.W,
+                                              a.top_idx, a.tape, a.seed, a.gen, a.P, a.W, T,
                                               reinterpret_cast<float4*>(a.next), a.next_fit, a.next_coll, a.sel, a.cpo);
     TF_LAUNCH_CHECK();
     return TF_OK;
