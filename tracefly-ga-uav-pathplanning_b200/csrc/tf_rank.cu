@@ -20,6 +20,9 @@ struct Key32 {  // fitness f32: one u64 = (~orderable(f) << 32) | idx
     __device__ __forceinline__ static Key32 pad() { return Key32{~0ull}; }
     __device__ __forceinline__ uint32_t index(bool worst) const { return (uint32_t)(worst ? ~v : v); }
     __device__ __forceinline__ bool operator<(const Key32& o) const { return v < o.v; }
+    __device__ __forceinline__ bool operator==(const Key32& o) const { return v == o.v; }
+    __device__ __forceinline__ bool is_pad() const { return v == ~0ull; }
+    __device__ __forceinline__ void shfl_xor(int m) { v = __shfl_xor_sync(0xffffffffu, v, m); }
 };
 
 struct Key64 {  // fitness f64: (~orderable(f), idx)
@@ -36,6 +39,12 @@ struct Key64 {  // fitness f64: (~orderable(f), idx)
     __device__ __forceinline__ static Key64 pad() { return Key64{~0ull, ~0ull}; }
     __device__ __forceinline__ uint32_t index(bool worst) const { return (uint32_t)(worst ? ~lo : lo); }
     __device__ __forceinline__ bool operator<(const Key64& o) const { return hi < o.hi || (hi == o.hi && lo < o.lo); }
+    __device__ __forceinline__ bool operator==(const Key64& o) const { return hi == o.hi && lo == o.lo; }
+    __device__ __forceinline__ bool is_pad() const { return hi == ~0ull && lo == ~0ull; }
+    __device__ __forceinline__ void shfl_xor(int m) {
+        hi = __shfl_xor_sync(0xffffffffu, hi, m);
+        lo = __shfl_xor_sync(0xffffffffu, lo, m);
+    }
 };
 
 constexpr int kRankThreads = 256;
@@ -75,10 +84,161 @@ topk_tile_kernel(const T* __restrict__ values, const Key* __restrict__ keys_in, 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Small k (the per-generation ranking: HR:115 top-2, HR:118 top-10): k rounds of a block-wide
+// arg-min over keys held in registers (8 per thread, 2048 per block) instead of a full sort.
+constexpr int kSmallItems = 8;
+constexpr int kSmallTile = kRankThreads * kSmallItems;
+constexpr int kSmallKMax = 16;
+
+template <typename Key, typename T>
+__global__ void __launch_bounds__(kRankThreads)
+topk_small_kernel(const T* __restrict__ values, const Key* __restrict__ keys_in, int n, int k, int worst,
+                  Key* __restrict__ keys_out, int32_t* __restrict__ idx_out) {
+    __shared__ Key wbest[kRankThreads / 32];
+    __shared__ Key winner;
+    Key mine[kSmallItems];
+    const int base = blockIdx.x * kSmallTile;
+#pragma unroll
+    for (int i = 0; i < kSmallItems; ++i) {
+        const int g = base + i * kRankThreads + threadIdx.x;
+        mine[i] = Key::pad();
+        if (g < n) mine[i] = values ? Key::make(values[g], (uint32_t)g, worst != 0) : keys_in[g];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = 0; r < k; ++r) {
+        Key best = mine[0];
+#pragma unroll
+        for (int i = 1; i < kSmallItems; ++i)
+            if (mine[i] < best) best = mine[i];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            Key o = best;
+            o.shfl_xor(m);
+            if (o < best) best = o;
+        }
+        if (lane == 0) wbest[warp] = best;
+        __syncthreads();
+        if (warp == 0) {
+            Key b = lane < kRankThreads / 32 ? wbest[lane] : Key::pad();
+#pragma unroll
+            for (int m = 4; m >= 1; m >>= 1) {
+                Key o = b;
+                o.shfl_xor(m);
+                if (o < b) b = o;
+            }
+            if (lane == 0) {
+                winner = b;
+                if (idx_out) idx_out[r] = b.is_pad() ? -1 : (int32_t)b.index(worst != 0);
+                else keys_out[(size_t)blockIdx.x * k + r] = b;
+            }
+        }
+        __syncthreads();
+        const Key w = winner;
+#pragma unroll
+        for (int i = 0; i < kSmallItems; ++i)
+            if (mine[i] == w) mine[i] = Key::pad();  // keys are unique: exactly one owner retires it
+    }
+}
+
 static int tile_for(int k) {
     int t = 2048;
     while (t < 2 * k) t <<= 1;
     return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// Large k (elite migration: E = 1024 elites, (world-1)*E worst): MSD radix SELECT on the 64-bit
+// composite key.  The keys are unique (the index is the low word), so six digit passes pin the
+// exact k-th key K; one compaction pass collects the k keys <= K and a single tile sort orders
+// them.  ~15 short launches that each read 4 B / chromosome, independent of k.
+constexpr int kSelPasses = 6;
+constexpr int kSelBins = 2048;
+struct SelState {
+    unsigned long long prefix;  // digits chosen so far (high bits of K)
+    int need;                   // rank of K inside the current prefix bucket (1-based)
+    unsigned int count;         // compaction cursor
+};
+__host__ __device__ __forceinline__ int sel_shift(int pass) { return pass < 5 ? 53 - 11 * pass : 0; }
+__host__ __device__ __forceinline__ int sel_width(int pass) { return pass < 5 ? 11 : 9; }
+
+__global__ void sel_init_kernel(SelState* st, unsigned int* hist, int k) {
+    for (int i = threadIdx.x; i < kSelPasses * kSelBins; i += blockDim.x) hist[i] = 0;
+    if (threadIdx.x == 0) { st->prefix = 0; st->need = k; st->count = 0; }
+}
+
+__global__ void __launch_bounds__(256)
+sel_hist_kernel(const float* __restrict__ values, int P, int worst, int pass, const SelState* __restrict__ st,
+                unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[kSelBins];
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int shift = sel_shift(pass), width = sel_width(pass);
+    const unsigned long long prefix = st->prefix;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = Key32::make(values[i], (uint32_t)i, worst != 0).v;
+        const bool match = pass == 0 || (key >> (shift + width)) == prefix;
+        if (match) atomicAdd(&sh[(unsigned)(key >> shift) & ((1u << width) - 1u)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[pass * kSelBins + i], sh[i]);
+}
+
+// one block of 256 threads: pick the digit whose cumulative count reaches `need`
+__global__ void __launch_bounds__(256) sel_scan_kernel(int pass, SelState* st, const unsigned int* __restrict__ hist) {
+    __shared__ unsigned int part[256];
+    const unsigned int* h = hist + pass * kSelBins;
+    const int nb = 1 << sel_width(pass);
+    const int per = kSelBins / 256;  // 8 bins per thread
+    unsigned int loc[per];
+    unsigned int sum = 0;
+#pragma unroll
+    for (int i = 0; i < per; ++i) {
+        const int b = threadIdx.x * per + i;
+        loc[i] = b < nb ? h[b] : 0u;
+        sum += loc[i];
+    }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {  // inclusive Hillis-Steele scan
+        unsigned int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const unsigned int need = (unsigned int)st->need;
+    const unsigned int before = threadIdx.x ? part[threadIdx.x - 1] : 0u;
+    const bool last = threadIdx.x == 255;
+    __syncthreads();
+    if ((before < need && need <= part[threadIdx.x]) || (last && need > part[255])) {
+        unsigned int run = before;
+        int i = 0;
+        for (; i < per - 1; ++i) {
+            if (run + loc[i] >= need) break;
+            run += loc[i];
+        }
+        int b = threadIdx.x * per + i;
+        if (b > nb - 1) b = nb - 1;
+        st->need = (int)(need - run);
+        st->prefix = (st->prefix << sel_width(pass)) | (unsigned long long)b;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sel_collect_kernel(const float* __restrict__ values, int P, int worst, int k, SelState* st, Key32* __restrict__ out) {
+    const unsigned long long K = st->prefix;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+        const Key32 key = Key32::make(values[i], (uint32_t)i, worst != 0);
+        if (key.v <= K) {
+            const unsigned int pos = atomicAdd(&st->count, 1u);
+            if (pos < (unsigned int)k) out[pos] = key;
+        }
+    }
+}
+
+static int64_t select_workspace_bytes(int k) {
+    return 256 + 256 + (int64_t)kSelPasses * kSelBins * 4 + (int64_t)k * 8 + 256;
 }
 
 template <typename Key>
@@ -86,8 +246,40 @@ static int64_t workspace_bytes(int P, int k) {
     const int tile = tile_for(k);
     int64_t n1 = (int64_t)((P + tile - 1) / tile) * k;
     int64_t n2 = ((n1 + tile - 1) / tile) * k;
-    return (n1 + n2) * (int64_t)sizeof(Key) + 256;
+    int64_t tiles = (n1 + n2) * (int64_t)sizeof(Key) + 256;
+    int64_t sel = select_workspace_bytes(k);
+    return tiles > sel ? tiles : sel;
 }
+
+static bool use_select(int P, int k) { return k > 64 && P > 4 * tile_for(k); }
+
+static int run_select(const float* values, int P, int k, int worst, int32_t* idx, void* ws, int64_t ws_bytes,
+                      cudaStream_t st) {
+    if (!ws || ws_bytes < select_workspace_bytes(k)) return TF_ERR_WORKSPACE;
+    char* base = reinterpret_cast<char*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    SelState* state = reinterpret_cast<SelState*>(base);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(base + 256);
+    Key32* keys = reinterpret_cast<Key32*>(base + 256 + kSelPasses * kSelBins * 4);
+    sel_init_kernel<<<1, 256, 0, st>>>(state, hist, k);
+    TF_LAUNCH_CHECK();
+    const int grid = min((P + 255) / 256, sm_count() * 8);
+    for (int pass = 0; pass < kSelPasses; ++pass) {
+        sel_hist_kernel<<<grid, 256, 0, st>>>(values, P, worst, pass, state, hist);
+        TF_LAUNCH_CHECK();
+        sel_scan_kernel<<<1, 256, 0, st>>>(pass, state, hist);
+        TF_LAUNCH_CHECK();
+    }
+    sel_collect_kernel<<<grid, 256, 0, st>>>(values, P, worst, k, state, keys);
+    TF_LAUNCH_CHECK();
+    const int tile = tile_for(k);
+    const size_t smem = (size_t)tile * sizeof(Key32);
+    auto kern = topk_tile_kernel<Key32, float>;
+    if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, kRankThreads, smem, st>>>(nullptr, keys, k, tile, k, worst, nullptr, idx);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+static int run_select(const double*, int, int, int, int32_t*, void*, int64_t, cudaStream_t) { return TF_ERR_UNSUPPORTED; }
 
 template <typename Key, typename T>
 static int run_topk(const T* values, int P, int k, int worst, int32_t* idx, void* ws, int64_t ws_bytes, cudaStream_t st) {
@@ -98,6 +290,34 @@ static int run_topk(const T* values, int P, int k, int worst, int32_t* idx, void
     if (smem > 200 * 1024) return TF_ERR_SHAPE;
     int rc = ensure_device();
     if (rc != TF_OK) return rc;
+    if (sizeof(Key) == 8 && use_select(P, k)) return run_select(values, P, k, worst, idx, ws, ws_bytes, st);
+    if (k <= kSmallKMax) {
+        auto small = topk_small_kernel<Key, T>;
+        int nb = (P + kSmallTile - 1) / kSmallTile;
+        if (nb == 1) {
+            small<<<1, kRankThreads, 0, st>>>(values, nullptr, P, k, worst, nullptr, idx);
+            TF_LAUNCH_CHECK();
+            return TF_OK;
+        }
+        if (!ws || ws_bytes < workspace_bytes<Key>(P, k)) return TF_ERR_WORKSPACE;
+        Key* a = reinterpret_cast<Key*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+        Key* b = a + (int64_t)nb * k;
+        small<<<nb, kRankThreads, 0, st>>>(values, nullptr, P, k, worst, a, nullptr);
+        TF_LAUNCH_CHECK();
+        int n = nb * k;
+        while (true) {
+            nb = (n + kSmallTile - 1) / kSmallTile;
+            if (nb == 1) {
+                small<<<1, kRankThreads, 0, st>>>(nullptr, a, n, k, worst, nullptr, idx);
+                TF_LAUNCH_CHECK();
+                return TF_OK;
+            }
+            small<<<nb, kRankThreads, 0, st>>>(nullptr, a, n, k, worst, b, nullptr);
+            TF_LAUNCH_CHECK();
+            n = nb * k;
+            Key* t = a; a = b; b = t;
+        }
+    }
     auto kern = topk_tile_kernel<Key, T>;
     if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int nblocks = (P + tile - 1) / tile;
