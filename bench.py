@@ -226,7 +226,10 @@ def run_gpu(args):
     launches = L.launch_count() - launches0
     clocks = sampler.finish()
     ms_total = t0.elapsed_time(t1)
-    gen_ms = float(np.mean([a.elapsed_time(b) for a, b in gen_ev]))
+    gen_times = [a.elapsed_time(b) for a, b in gen_ev]
+    gen_ms = float(np.mean(gen_times))
+    q = max(1, len(gen_times) // 4)
+    gen_ms_first, gen_ms_last = float(np.mean(gen_times[:q])), float(np.mean(gen_times[-q:]))
     if world > 1:
         t = torch.tensor([ms_total], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -296,6 +299,7 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "kernel": "generation_kernel (tf_generation)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_unit": bpu, "kernel_ms": gen_ms,
+                     "kernel_ms_first_quarter": gen_ms_first, "kernel_ms_last_quarter": gen_ms_last,
                      "kernel_share_of_step": gen_ms / (ms_total / args.steps)},
         "clocks": clocks, "gpu_launches": int(launches),
     }
