@@ -247,6 +247,10 @@ int tf_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_byt
 /* Philox4x32-10 block, exposed so host code and tests can reproduce device draws. */
 void tf_philox4x32_10(uint32_t key0, uint32_t key1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                       uint32_t out[4]);
+/* Options.  TF_OPT_DISABLE_STREAM = 1 forces the LSU-path kernels even where the TMA-staged
+ * kernels apply (W = 32 / 64 / 128, fixed length); both give bit-identical results. */
+#define TF_OPT_DISABLE_STREAM 1
+int tf_set_option(int option, int value);
 /* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
 int64_t tf_launch_count(void);
 

@@ -191,3 +191,42 @@ def test_init_populations(tf):
     got = B.init_walks(77, 1000, 33, lo=(0, 0, 0), hi=(49, 49, 49), start_per_path=starts)
     exp = O.init_walks(77, 1000, 33, (0, 0, 0), (0, 0, 0), (49, 49, 49), start_pp=starts.cpu().numpy())
     assert np.array_equal(exp, got.cpu().numpy())
+
+
+@pytest.mark.parametrize("W", [32, 64, 128])
+@pytest.mark.parametrize("env_kind", ["none", "pf", "vox+dyn+haz"])
+def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind):
+    """The TMA-staged kernels (W = 32/64/128) must give bit-identical results to the LSU-path kernels."""
+    torch, L, B = tf
+    P = 5003
+    rng = np.random.default_rng(W)
+    dims = (64, 64, 64)
+    table = random_table(rng, 150, 64, sem_pf=True)
+    if env_kind == "none":
+        env = B.Environment.empty()
+    elif env_kind == "pf":
+        env = B.Environment(L.SEM_PF, table, 0.0)
+    else:
+        env = B.Environment(L.SEM_HR, table[:40], 2.0).set_voxels(B.voxelize(table, dims, L.SEM_PF), dims)
+        dyn = np.zeros((16, 8), np.float32)
+        dyn[:, :3] = rng.uniform(0, 64, size=(16, 3))
+        dyn[:, 3] = 2
+        dyn[:, 4:7] = rng.uniform(-1, 1, size=(16, 3))
+        env.set_dynamic(dyn, 1.0)
+        env.set_hazard(torch.from_numpy(rng.uniform(0, 1, size=(8, 16, 16)).astype(np.float32)).cuda(), 0.25, 0.25, 0, 0, 7.0 / (W - 1))
+    prm = L.default_params(hazard_weight=0.3)
+    pop = B.init_walks(5, P, W, start=(32, 32, 32), lo=(0, 0, 0), hi=(63, 63, 63))
+    ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=3, mutation_rate=0.5, n_elite=3)
+    res = {}
+    for disable in (0, 1):
+        L.set_option(L.OPT_DISABLE_STREAM, disable)
+        try:
+            fit, coll = B.fitness_batch(pop, None, env, prm)
+            top = B.rank_topk(fit, 3)
+            out = B.generation(env, pop, fit, top, ga, prm, seed=77, generation=9, want_collisions=True, want_parity=True)
+            torch.cuda.synchronize()
+            res[disable] = (fit, coll) + out
+        finally:
+            L.set_option(L.OPT_DISABLE_STREAM, 0)
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)

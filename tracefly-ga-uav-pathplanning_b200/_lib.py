@@ -76,6 +76,7 @@ _SIGS = {
     "tf_last_cuda_error": (_i, []),
     "tf_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i64)]),
     "tf_philox4x32_10": (None, [_u32, _u32, _u32, _u32, _u32, _u32, C.POINTER(_u32)]),
+    "tf_set_option": (_i, [_i, _i]),
     "tf_launch_count": (_i64, []),
 }
 for _name, (_res, _args) in _SIGS.items():
@@ -123,6 +124,13 @@ def philox(key0, key1, c0, c1, c2, c3):
     out = (C.c_uint32 * 4)()
     lib.tf_philox4x32_10(key0, key1, c0, c1, c2, c3, out)
     return [int(v) for v in out]
+
+
+OPT_DISABLE_STREAM = 1
+
+
+def set_option(option, value):
+    check(lib.tf_set_option(option, int(value)), "tf_set_option")
 
 
 def launch_count():

@@ -12,6 +12,7 @@ namespace tf {
 
 thread_local int g_last_cuda_error = 0;
 long long g_launch_count = 0;
+int g_disable_stream = 0;
 static int g_sm_count = 0;
 static int g_dev_checked = 0;
 
@@ -320,6 +321,11 @@ extern "C" void tf_philox4x32_10(uint32_t key0, uint32_t key1, uint32_t c0, uint
                                  uint32_t out[4]) {
     tf::U4 r = tf::philox4x32_10(key0, key1, c0, c1, c2, c3);
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+extern "C" int tf_set_option(int option, int value) {
+    if (option == TF_OPT_DISABLE_STREAM) { tf::g_disable_stream = value != 0; return TF_OK; }
+    return TF_ERR_INVALID;
 }
 
 extern "C" int64_t tf_launch_count(void) { return (int64_t)tf::g_launch_count; }

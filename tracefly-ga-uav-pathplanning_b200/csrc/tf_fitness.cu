@@ -1,6 +1,7 @@
 // tf_fitness.cu — tf_fitness (FP32, one warp per chromosome) and tf_fitness_f64
 // (reference-order float64, one thread per chromosome).
 #include "tf_fitness_dev.cuh"
+#include "tf_stream_dev.cuh"
 
 namespace tf {
 
@@ -267,6 +268,13 @@ extern "C" int tf_fitness(const tf_env* env, const float* pop_dev, const int32_t
     if ((rc = ensure_device()) != TF_OK) return rc;
     if (P == 0) return TF_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (lens_dev == nullptr && stream_eligible(env->d, W, false) && !g_disable_stream) {
+        tf_ga_params ga_unused;
+        tf_ga_params_default(&ga_unused);
+        StreamArgs sa{&env->d, params, &ga_unused, pop_dev, nullptr, nullptr, nullptr, 0, 0, P, W,
+                      nullptr, fit_dev, coll_dev, nullptr, nullptr, st};
+        return stream_dispatch<false>(sa);
+    }
     const int nw = (W + 31) / 32;
     if (nw <= 1) return dispatch_sem<1>(env->d, *params, pop_dev, lens_dev, P, W, fit_dev, coll_dev, st);
     if (nw <= 2) return dispatch_sem<2>(env->d, *params, pop_dev, lens_dev, P, W, fit_dev, coll_dev, st);

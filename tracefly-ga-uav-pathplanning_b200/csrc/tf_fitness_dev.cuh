@@ -139,6 +139,24 @@ __device__ __forceinline__ bool voxel_hit(const EnvDev& e, float x, float y, flo
     return (w >> (((iy & 3) << 3) | (ix & 7))) & 1u;
 }
 
+// The same probe split in two so that the gather can be issued one chromosome ahead of its use:
+// voxel_prefetch issues the loads (word + single-bit mask per slot), the consumer tests word & mask.
+template <int NW>
+struct VoxRegs {
+    uint32_t word[NW], mask[NW];
+};
+template <int NW>
+__device__ __forceinline__ void voxel_prefetch(const EnvDev& e, const Lanes<NW>& p, VoxRegs<NW>& v) {
+#pragma unroll
+    for (int s = 0; s < NW; ++s) {
+        const int ix = __float2int_rd(p.x[s]), iy = __float2int_rd(p.y[s]), iz = __float2int_rd(p.z[s]);
+        const bool inb = (unsigned)ix < (unsigned)e.nx && (unsigned)iy < (unsigned)e.ny && (unsigned)iz < (unsigned)e.nz;
+        const uint32_t brick = (uint32_t)(ix >> 3) + (uint32_t)e.nbx * ((uint32_t)(iy >> 3) + (uint32_t)e.nby * (uint32_t)(iz >> 3));
+        v.mask[s] = inb ? (1u << (((iy & 3) << 3) | (ix & 7))) : 0u;
+        v.word[s] = inb ? __ldg(e.bricks + (size_t)brick * 16 + ((iz & 7) * 2 + ((iy & 7) >> 2))) : 0u;
+    }
+}
+
 __device__ __forceinline__ float lerp_f(float a, float b, float f) { return fmaf(f, __fsub_rn(b, a), a); }
 
 // Tri-linear hazard lookup (extension; the unused wind_data hook of PF:144).

@@ -164,4 +164,56 @@ __device__ __forceinline__ ChildPlan<NW> plan_elite(int src, int L) {
     return pl;
 }
 
+// Phase-B plan broadcast: everything the 32 lanes need to move child c's waypoints.
+template <int NW>
+struct PlanB {
+    int first, second, cp, mp, L;
+    float dx, dy, dz;
+    uint32_t mask[NW];
+};
+template <int NW>
+__device__ __forceinline__ PlanB<NW> broadcast_plan(const ChildPlan<NW>& mine, int c, bool uniform) {
+    PlanB<NW> b;
+    b.first = __shfl_sync(0xffffffffu, mine.first, c);
+    b.second = __shfl_sync(0xffffffffu, mine.second, c);
+    const int meta = __shfl_sync(0xffffffffu, mine.meta, c);
+    b.cp = meta_cp(meta);
+    b.mp = meta_mp(meta);
+    b.L = meta_len(meta);
+    b.dx = b.dy = b.dz = 0.0f;
+    if (b.mp >= 0) {  // warp-uniform
+        b.dx = __shfl_sync(0xffffffffu, mine.dx, c);
+        b.dy = __shfl_sync(0xffffffffu, mine.dy, c);
+        b.dz = __shfl_sync(0xffffffffu, mine.dz, c);
+    }
+#pragma unroll
+    for (int s = 0; s < NW; ++s) b.mask[s] = uniform ? __shfl_sync(0xffffffffu, mine.mask[s], c) : 0u;
+    return b;
+}
+template <int NW>
+__device__ __forceinline__ bool from_first(const PlanB<NW>& b, int k, int s, int lane) {
+    return (k < b.cp) && !((b.mask[s] >> lane) & 1u);  // HR:87-88; uniform: cp = 511 and the mask decides
+}
+
+// Phase A for a tile: this lane's slot.
+template <int NW, typename F>
+__device__ __forceinline__ ChildPlan<NW> plan_slot(int slot, int ne, const F* fit, const int32_t* lens,
+                                                  const int32_t* top_idx, const tf_draw* tape, uint64_t seed,
+                                                  uint32_t gen, const tf_ga_params& ga, int P, int W,
+                                                  int32_t* sel, int32_t* cpo) {
+    if (slot >= P) return plan_elite<NW>(0, 0);
+    if (slot < ne) {  // HR:115 elitism
+        const int src = top_idx[slot];
+        return plan_elite<NW>(src, lens ? lens[src] : W);
+    }
+    ChildPlan<NW> pl = plan_child<NW, F>(slot, ne, fit, lens, top_idx, tape, seed, gen, ga, P, W);
+    if (((slot - ne) & 1) == 0) {
+        const int j = (slot - ne) >> 1;
+        if (sel) { sel[2 * j] = pl.ia; sel[2 * j + 1] = pl.ib; }
+        if (cpo) cpo[j] = (ga.crossover == TF_CX_UNIFORM && tape == nullptr) ? 0 : meta_cp(pl.meta);
+    }
+    return pl;
+}
+
+
 }  // namespace tf

@@ -1,0 +1,303 @@
+// tf_stream_dev.cuh — TMA-staged form of the FP32 fitness sweep / fused generation for
+// chromosomes of exactly 32*NW waypoints (the BASELINE configs: W = 32, 64).
+//
+// Same tile structure and the SAME arithmetic (bit-identical results) as fitness_kernel /
+// generation_kernel, but the rows never pass through the LSU on the way in:
+//   * each warp owns a ring of kStages row buffers in shared memory, each with its own mbarrier;
+//   * one elected lane issues, kStages-2 chromosomes ahead, the 1-D TMA bulk copies that gather a
+//     child's two parent pieces ([0,cp) of one parent, [cp,W) of the other) straight into a ring
+//     slot (cp.async.bulk ... mbarrier::complete_tx — SASS UBLKCP);
+//   * the mutation is applied in shared memory, the voxel gathers of chromosome c+1 are issued
+//     before chromosome c is evaluated, and the neighbour waypoint is a second LDS instead of
+//     three shuffles.
+// What is in flight is now bounded by shared memory (kStages-2 KB-sized rows per warp), not by
+// registers, so the DRAM latency of the random parent gathers is hidden at 32 warps / SM.
+#pragma once
+#include "tf_fitness_dev.cuh"
+#include "tf_ga_dev.cuh"
+
+namespace tf {
+
+constexpr int kStages = 6;
+
+__host__ __device__ inline size_t stream_smem_bytes(const EnvDev& e, int W) {
+    size_t tables = (smem_bytes_for(e) + 127) & ~(size_t)127;
+    return tables + (size_t)kWarpsPerBlock * kStages * W * 16 + (size_t)kWarpsPerBlock * kStages * 8;
+}
+
+// Score bookkeeping of one full-length chromosome whose waypoints sit in shared memory.
+template <int NW, int SEM, bool VOX, bool EXTRA>
+__device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& prm, const Tables& t,
+                                             const Lanes<NW>& cur, const Lanes<NW>& prev, const uint32_t (&vword)[NW],
+                                             const uint32_t (&vmask)[NW], PointAcc<NW, SEM>& acc, int c,
+                                             TileSums<NW>& out) {
+    constexpr int W = 32 * NW;
+    const int lane = threadIdx.x & 31;
+    float a_prox = 0.0f, a_dist = 0.0f, a_alt = 0.0f, a_haz = 0.0f;
+    int turns = 0, ncoll = 0;
+    uint32_t hit = acc.hit;
+    const bool has_dist = (SEM != TF_SEM_NONE) || (EXTRA && e.n_dyn > 0);
+    float dn[NW];
+#pragma unroll
+    for (int s = 0; s < NW; ++s) dn[s] = (SEM == TF_SEM_HR) ? __fsqrt_rn(acc.best[s]) : acc.best[s];
+    if constexpr (EXTRA) {
+        if (e.n_dyn > 0) {
+            float m2[NW], tm[NW];
+#pragma unroll
+            for (int s = 0; s < NW; ++s) {
+                m2[s] = INFINITY;
+                tm[s] = (float)(lane + 32 * s);
+            }
+            eval_dynamic<NW>(e, t, cur.x, cur.y, cur.z, tm, hit, m2);
+#pragma unroll
+            for (int s = 0; s < NW; ++s) dn[s] = fminf(dn[s], __fsqrt_rn(m2[s]));
+        }
+    }
+    const int S = EXTRA ? max(prm.samples_per_segment, 1) : 1;
+#pragma unroll
+    for (int s = 0; s < NW; ++s) {
+        const int k = lane + 32 * s;
+        bool h = (hit >> s) & 1u;
+        if constexpr (VOX) h = h || (vword[s] & vmask[s]) != 0u;
+        const uint32_t word = __ballot_sync(0xffffffffu, h);
+        if (lane == c) out.cw[s] = word;
+        ncoll += h ? 1 : 0;
+        if (has_dist) a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[s])));  // HR:46
+        if constexpr (EXTRA) {
+            if (e.hazard != nullptr) a_haz = __fadd_rn(a_haz, hazard_sample(e, cur.x[s], cur.y[s], (float)k));
+        }
+        if (s > 0 || lane > 0) {  // k >= 1
+            const float px = prev.x[s], py = prev.y[s], pz = prev.z[s];
+            const float dx = cur.x[s] - px, dy = cur.y[s] - py, dz = cur.z[s] - pz;
+            a_dist = __fadd_rn(a_dist, __fsqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
+            a_alt = __fadd_rn(a_alt, fabsf(dz));                         // HR:44
+            if (k <= W - 2) turns += (cur.x[s] != px || cur.y[s] != py) ? 1 : 0;  // HR:38-40,43
+            if constexpr (EXTRA) {
+                for (int j = 1; j < S; ++j) {  // extension: samples inside segment (k-1, k)
+                    float tj = __fdiv_rn((float)j, (float)S);
+                    bool sh;
+                    float sdn;
+                    eval_point_full<SEM, VOX, EXTRA>(e, t, fmaf(dx, tj, px), fmaf(dy, tj, py), fmaf(dz, tj, pz),
+                                                     __fadd_rn((float)(k - 1), tj), sh, sdn);
+                    ncoll += sh ? 1 : 0;
+                    if (has_dist) a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, sdn)));
+                }
+            }
+        }
+    }
+    const float dist = warp_sum_xor(a_dist), alt = warp_sum_xor(a_alt);
+    const int packed = __reduce_add_sync(0xffffffffu, turns | (ncoll << 10));
+    if (lane == c) { out.dist = dist; out.alt = alt; out.packed = packed; }
+    if (has_dist) {
+        const float prox = warp_sum_xor(a_prox);
+        if (lane == c) out.prox = prox;
+    }
+    if constexpr (EXTRA) {
+        if (e.hazard != nullptr) {
+            const float haz = warp_sum_xor(a_haz);
+            if (lane == c) out.haz = haz;
+        }
+    }
+}
+
+// GA = true : fused generation (plan, gather both parents, mutate, store child, evaluate)
+// GA = false: fitness sweep (row p, no store)
+template <int NW, int SEM, bool VOX, bool EXTRA, bool GA>
+__global__ void __launch_bounds__(kBlockThreads)
+stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
+              const __grid_constant__ tf_ga_params ga, const float4* __restrict__ pop,
+              const float* __restrict__ fit, const int32_t* __restrict__ top_idx,
+              const tf_draw* __restrict__ tape, uint64_t seed, uint32_t gen, int P, int T,
+              float4* __restrict__ next, float* __restrict__ out_fit, uint32_t* __restrict__ out_coll,
+              int32_t* __restrict__ sel, int32_t* __restrict__ cpo) {
+    constexpr int W = 32 * NW;
+    extern __shared__ __align__(128) unsigned char smem_stream[];
+    unsigned char* smem = smem_stream;
+    const SmemLayout sm = carve_smem(e, smem);
+    const Tables tabs{sm.A, sm.B, sm.dA, sm.dB};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t tables = (smem_bytes_for(e) + 127) & ~(size_t)127;
+    float4* ring = reinterpret_cast<float4*>(smem + tables) + (size_t)warp * kStages * W;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tables + (size_t)kWarpsPerBlock * kStages * W * 16) + warp * kStages;
+    const int ne = GA ? min(ga.n_elite, P) : 0;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);
+    }
+    if ((SEM != TF_SEM_NONE && e.n > 0) || (EXTRA && e.n_dyn > 0)) {
+        if (threadIdx.x == 0) mbar_init(sm.bar, 1);
+        fence_mbar_init();
+        __syncthreads();
+        if (threadIdx.x == 0)
+            stage_chunk(e, sm.A, sm.B, 0, min(e.n, kTableCap), sm.bar, EXTRA && e.n_dyn > 0, sm.dA, sm.dB);
+        mbar_wait(sm.bar, 0);
+    } else {
+        fence_mbar_init();
+        __syncwarp();
+    }
+
+    uint32_t seq = 0;  // chromosomes this warp has pushed through its ring so far
+    const int ntiles = (P + T - 1) / T;
+    for (int tile = blockIdx.x * kWarpsPerBlock + warp; tile < ntiles; tile += gridDim.x * kWarpsPerBlock) {
+        const int slot0 = tile * T;
+        const int cnt = min(T, P - slot0);
+        // ---- phase A (lane = slot)
+        ChildPlan<NW> mine;
+        if constexpr (GA) {
+            mine = plan_slot<NW, float>(lane < T ? slot0 + lane : P, ne, fit, nullptr, top_idx, tape, seed, gen, ga, P, W, sel, cpo);
+        } else {
+            mine = plan_elite<NW>(min(slot0 + lane, P - 1), W);
+        }
+        TileSums<NW> sums;
+        sums.reset();
+
+        auto stage_of = [&](int c) { return (int)((seq + (uint32_t)c) % kStages); };
+        auto parity_of = [&](int c) { return ((seq + (uint32_t)c) / kStages) & 1u; };
+
+        // gather child c's two parent pieces into its ring slot (one elected lane issues the TMA)
+        auto issue = [&](int c) {
+            const int first = __shfl_sync(0xffffffffu, mine.first, c);
+            const int second = __shfl_sync(0xffffffffu, mine.second, c);
+            const int meta = __shfl_sync(0xffffffffu, mine.meta, c);
+            if (lane == 0) {
+                const int st = stage_of(c);
+                const int cpc = min(meta_cp(meta), W);
+                float4* dst = ring + st * W;
+                mbar_expect_tx(&bars[st], (uint32_t)W * 16u);
+                if (cpc > 0) tma_load_1d(dst, pop + (size_t)first * W, (uint32_t)cpc * 16u, &bars[st]);
+                if (cpc < W) tma_load_1d(dst + cpc, pop + (size_t)second * W + cpc, (uint32_t)(W - cpc) * 16u, &bars[st]);
+            }
+        };
+
+        // wait for child c's row, apply its mutation in shared memory, start its voxel gathers
+        auto prepare = [&](int c, uint32_t (&vword)[NW], uint32_t (&vmask)[NW]) {
+            const int st = stage_of(c);
+            float4* row = ring + st * W;
+            mbar_wait(&bars[st], parity_of(c));
+            if constexpr (GA) {
+                const int mp = meta_mp(__shfl_sync(0xffffffffu, mine.meta, c));
+                if (mp >= 0) {  // warp-uniform; HR:97-98
+                    const float dx = __shfl_sync(0xffffffffu, mine.dx, c);
+                    const float dy = __shfl_sync(0xffffffffu, mine.dy, c);
+                    const float dz = __shfl_sync(0xffffffffu, mine.dz, c);
+                    if (lane == (mp & 31)) {
+                        float4 v = row[mp];
+                        v.x = __fadd_rn(v.x, dx);
+                        v.y = __fadd_rn(v.y, dy);
+                        v.z = __fadd_rn(v.z, dz);
+                        row[mp] = v;
+                    }
+                    __syncwarp();
+                }
+            }
+            if constexpr (VOX) {
+                Lanes<NW> p;
+#pragma unroll
+                for (int s = 0; s < NW; ++s) {
+                    const float4 v = row[lane + 32 * s];
+                    p.x[s] = v.x; p.y[s] = v.y; p.z[s] = v.z;
+                }
+                VoxRegs<NW> vr;
+                voxel_prefetch<NW>(e, p, vr);
+#pragma unroll
+                for (int s = 0; s < NW; ++s) { vword[s] = vr.word[s]; vmask[s] = vr.mask[s]; }
+            }
+        };
+
+        const int pre = min(cnt, kStages);
+        for (int c = 0; c < pre; ++c) issue(c);
+        uint32_t v0w[NW], v0m[NW], v1w[NW], v1m[NW];
+#pragma unroll
+        for (int s = 0; s < NW; ++s) v0w[s] = v0m[s] = v1w[s] = v1m[s] = 0u;
+        prepare(0, v0w, v0m);
+#pragma unroll 1
+        for (int c = 0; c < cnt; ++c) {
+            if (c + 1 < cnt) prepare(c + 1, v1w, v1m);
+            const float4* row = ring + stage_of(c) * W;
+            Lanes<NW> cur, prev;
+            float4* dst = GA ? next + (size_t)(slot0 + c) * W : nullptr;
+#pragma unroll
+            for (int s = 0; s < NW; ++s) {
+                const int k = lane + 32 * s;
+                const float4 v = row[k];
+                const float4 q = row[k > 0 ? k - 1 : 0];
+                cur.x[s] = v.x; cur.y[s] = v.y; cur.z[s] = v.z;
+                prev.x[s] = q.x; prev.y[s] = q.y; prev.z[s] = q.z;
+                if constexpr (GA) stg_stream(dst + k, v);
+            }
+            PointAcc<NW, SEM> acc;
+            acc.reset();
+            if constexpr (SEM != TF_SEM_NONE) eval_static_chunk<SEM, NW>(e, tabs, 0, e.n, cur.x, cur.y, cur.z, acc.hit, acc.best);
+            reduce_fullw<NW, SEM, VOX, EXTRA>(e, prm, tabs, cur, prev, v0w, v0m, acc, c, sums);
+            __syncwarp();  // every lane is done with this ring slot: refill it
+            if (c + kStages < cnt) issue(c + kStages);
+#pragma unroll
+            for (int s = 0; s < NW; ++s) { v0w[s] = v1w[s]; v0m[s] = v1m[s]; }
+        }
+        seq += (uint32_t)cnt;
+        // ---- phase C (lane = slot)
+        if (lane < cnt) {
+            const int slot = slot0 + lane;
+            out_fit[slot] = combine_fitness<NW, EXTRA>(e, prm, sums);
+            if (out_coll) {
+#pragma unroll
+                for (int s = 0; s < NW; ++s) out_coll[(size_t)slot * NW + s] = sums.cw[s];
+            }
+        }
+    }
+}
+
+struct StreamArgs {
+    const EnvDev* e; const tf_params* prm; const tf_ga_params* ga; const float* pop; const float* fit;
+    const int32_t* top_idx; const tf_draw* tape; uint64_t seed; uint32_t gen; int P, W;
+    float* next; float* out_fit; uint32_t* out_coll; int32_t* sel; int32_t* cpo; cudaStream_t st;
+};
+
+template <int NW, int SEM, bool VOX, bool EXTRA, bool GA>
+static int launch_stream(const StreamArgs& a) {
+    auto kern = stream_kernel<NW, SEM, VOX, EXTRA, GA>;
+    const size_t smem = stream_smem_bytes(*a.e, a.W);
+    if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int T = tile_size_for(a.P);
+    const int ntiles = (a.P + T - 1) / T;
+    const int grid = min((ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
+    kern<<<grid, kBlockThreads, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
+                                              a.top_idx, a.tape, a.seed, a.gen, a.P, T,
+                                              reinterpret_cast<float4*>(a.next), a.out_fit, a.out_coll, a.sel, a.cpo);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+template <int NW, int SEM, bool GA>
+static int stream_flags(const StreamArgs& a) {
+    const bool vox = a.e->bricks != nullptr;
+    const bool extra = a.e->n_dyn > 0 || a.e->hazard != nullptr || a.prm->samples_per_segment > 1;
+    if (vox && extra) return launch_stream<NW, SEM, true, true, GA>(a);
+    if (vox) return launch_stream<NW, SEM, true, false, GA>(a);
+    if (extra) return launch_stream<NW, SEM, false, true, GA>(a);
+    return launch_stream<NW, SEM, false, false, GA>(a);
+}
+template <int NW, bool GA>
+static int stream_sem(const StreamArgs& a) {
+    switch (a.e->n > 0 ? a.e->semantics : TF_SEM_NONE) {
+    case TF_SEM_HR: return stream_flags<NW, TF_SEM_HR, GA>(a);
+    case TF_SEM_PF: return stream_flags<NW, TF_SEM_PF, GA>(a);
+    default: return stream_flags<NW, TF_SEM_NONE, GA>(a);
+    }
+}
+template <bool GA>
+static int stream_dispatch(const StreamArgs& a) {
+    switch (a.W / 32) {
+    case 1: return stream_sem<1, GA>(a);
+    case 2: return stream_sem<2, GA>(a);
+    default: return stream_sem<4, GA>(a);
+    }
+}
+
+// Host-side eligibility: full-length chromosomes, single table chunk, contiguous parent pieces.
+inline bool stream_eligible(const EnvDev& e, int W, bool uniform_mask) {
+    if (W % 32 != 0 || W > 128 || W == 96 || uniform_mask || e.n > kTableCap) return false;
+    return stream_smem_bytes(e, W) <= 200 * 1024;
+}
+
+}  // namespace tf
