@@ -169,7 +169,17 @@ def build_gpu_workload(cfg, rank, torch, B, L):
     return env, params, pop, ga
 
 
+def _claim_stdout():
+    """NCCL / driver libraries may printf to fd 1; keep fd 1 for the ONE JSON line by pointing the
+    process's stdout at stderr and returning a private handle to the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def run_gpu(args):
+    out = _claim_stdout()
     import torch
     import torch.distributed as dist
     from tracefly_b200 import _lib as L
@@ -200,6 +210,8 @@ def run_gpu(args):
 
     for _ in range(args.warmup):
         island.step()
+    if world > 1:
+        island.migrate()  # untimed: NCCL communicator set-up and first-collective connect happen here
     sync_all()
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream, max over ranks
@@ -307,7 +319,8 @@ def run_gpu(args):
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.workload, seconds=args.cpu_seconds)
-    print(json.dumps(line), flush=True)
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -137,7 +137,13 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
         __syncwarp();
     }
 
-    uint32_t seq = 0;  // chromosomes this warp has pushed through its ring so far
+    // ring bookkeeping without divisions: `head` = ring slot of the chromosome being evaluated,
+    // `phase` = one parity bit per slot (flips every time the slot's mbarrier completes a phase)
+    int head = 0;
+    uint32_t phase = 0;
+    const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
+    auto next_slot = [](int st) { return st + 1 == kStages ? 0 : st + 1; };
+
     const int ntiles = (P + T - 1) / T;
     for (int tile = blockIdx.x * kWarpsPerBlock + warp; tile < ntiles; tile += gridDim.x * kWarpsPerBlock) {
         const int slot0 = tile * T;
@@ -152,29 +158,30 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
         TileSums<NW> sums;
         sums.reset();
 
-        auto stage_of = [&](int c) { return (int)((seq + (uint32_t)c) % kStages); };
-        auto parity_of = [&](int c) { return ((seq + (uint32_t)c) / kStages) & 1u; };
-
-        // gather child c's two parent pieces into its ring slot (one elected lane issues the TMA)
-        auto issue = [&](int c) {
+        // gather child c's two parent pieces into ring slot st (one elected lane issues the TMA)
+        auto issue = [&](int c, int st) {
             const int first = __shfl_sync(0xffffffffu, mine.first, c);
             const int second = __shfl_sync(0xffffffffu, mine.second, c);
             const int meta = __shfl_sync(0xffffffffu, mine.meta, c);
             if (lane == 0) {
-                const int st = stage_of(c);
                 const int cpc = min(meta_cp(meta), W);
-                float4* dst = ring + st * W;
-                mbar_expect_tx(&bars[st], (uint32_t)W * 16u);
-                if (cpc > 0) tma_load_1d(dst, pop + (size_t)first * W, (uint32_t)cpc * 16u, &bars[st]);
-                if (cpc < W) tma_load_1d(dst + cpc, pop + (size_t)second * W + cpc, (uint32_t)(W - cpc) * 16u, &bars[st]);
+                const uint32_t dst = ring_u32 + (uint32_t)st * (W * 16u), bar = bars_u32 + (uint32_t)st * 8u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)W * 16u) : "memory");
+                if (cpc > 0)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                                 "l"(pop + (size_t)first * W), "r"((uint32_t)cpc * 16u), "r"(bar) : "memory");
+                if (cpc < W)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     dst + (uint32_t)cpc * 16u),
+                                 "l"(pop + (size_t)second * W + cpc), "r"((uint32_t)(W - cpc) * 16u), "r"(bar) : "memory");
             }
         };
 
-        // wait for child c's row, apply its mutation in shared memory, start its voxel gathers
-        auto prepare = [&](int c, uint32_t (&vword)[NW], uint32_t (&vmask)[NW]) {
-            const int st = stage_of(c);
+        // wait for child c's row (ring slot st), apply its mutation in shared memory, start its voxel gathers
+        auto prepare = [&](int c, int st, uint32_t (&vword)[NW], uint32_t (&vmask)[NW]) {
             float4* row = ring + st * W;
-            mbar_wait(&bars[st], parity_of(c));
+            mbar_wait(&bars[st], (phase >> st) & 1u);
+            phase ^= 1u << st;
             if constexpr (GA) {
                 const int mp = meta_mp(__shfl_sync(0xffffffffu, mine.meta, c));
                 if (mp >= 0) {  // warp-uniform; HR:97-98
@@ -205,16 +212,21 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
             }
         };
 
+        // all ring slots are free at a tile boundary: slots head, head+1, ... take children 0, 1, ...
         const int pre = min(cnt, kStages);
-        for (int c = 0; c < pre; ++c) issue(c);
+        {
+            int st = head;
+            for (int c = 0; c < pre; ++c) { issue(c, st); st = next_slot(st); }
+        }
         uint32_t v0w[NW], v0m[NW], v1w[NW], v1m[NW];
 #pragma unroll
         for (int s = 0; s < NW; ++s) v0w[s] = v0m[s] = v1w[s] = v1m[s] = 0u;
-        prepare(0, v0w, v0m);
+        prepare(0, head, v0w, v0m);
 #pragma unroll 1
         for (int c = 0; c < cnt; ++c) {
-            if (c + 1 < cnt) prepare(c + 1, v1w, v1m);
-            const float4* row = ring + stage_of(c) * W;
+            const int st_next = next_slot(head);
+            if (c + 1 < cnt) prepare(c + 1, st_next, v1w, v1m);
+            const float4* row = ring + head * W;
             Lanes<NW> cur, prev;
             float4* dst = GA ? next + (size_t)(slot0 + c) * W : nullptr;
 #pragma unroll
@@ -231,11 +243,11 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
             if constexpr (SEM != TF_SEM_NONE) eval_static_chunk<SEM, NW>(e, tabs, 0, e.n, cur.x, cur.y, cur.z, acc.hit, acc.best);
             reduce_fullw<NW, SEM, VOX, EXTRA>(e, prm, tabs, cur, prev, v0w, v0m, acc, c, sums);
             __syncwarp();  // every lane is done with this ring slot: refill it
-            if (c + kStages < cnt) issue(c + kStages);
+            if (c + kStages < cnt) issue(c + kStages, head);
+            head = st_next;
 #pragma unroll
             for (int s = 0; s < NW; ++s) { v0w[s] = v1w[s]; v0m[s] = v1m[s]; }
         }
-        seq += (uint32_t)cnt;
         // ---- phase C (lane = slot)
         if (lane < cnt) {
             const int slot = slot0 + lane;
