@@ -291,6 +291,14 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peak_gbs()
+    traffic = None
+    try:  # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f).get(args.workload)
+        if t and P == WORKLOADS[args.workload]["P"]:
+            traffic = t["dram_bytes_per_launch"]
+    except Exception:
+        pass
     bpu = algorithmic_bytes_per_unit(W)
     achieved = bpu * P * (W - 1) / (gen_ms * 1e-3) / 1e9
     line = {
@@ -308,8 +316,9 @@ def run_gpu(args):
                    "migration": f"{ELITES} elites NCCL all-gather every {MIGRATE_EVERY} generations" if world > 1 else "none (1 island)",
                    "l2": "inputs larger than L2: population 2 x %.0f MiB ping-pong, voxel grid %d MiB" % (
                        P * W * 16 / 2 ** 20, (cfg["world"][0] * cfg["world"][1] * cfg["world"][2] // 8) >> 20 if cfg["n_voxel_obs"] else 0)},
-        "roofline": {"bound": "hbm", "kernel": "generation_kernel (tf_generation)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "stream_kernel<GA> (tf_generation, TMA-staged)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bpu * P * (W - 1),
                      "algorithmic_bytes_per_unit": bpu, "kernel_ms": gen_ms,
                      "kernel_ms_first_quarter": gen_ms_first, "kernel_ms_last_quarter": gen_ms_last,
                      "kernel_share_of_step": gen_ms / (ms_total / args.steps)},

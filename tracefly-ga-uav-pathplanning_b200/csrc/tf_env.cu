@@ -134,6 +134,9 @@ static int upload_static(tf_env* env, int semantics, const std::vector<double>& 
     d.semantics = semantics;
     d.n = n;
     d.n_sphere = cnt[0]; d.n_cube = cnt[1]; d.n_cyl = cnt[2]; d.n_aabb = cnt[3];
+    d.smax_sc = 0.0f;
+    if (semantics == TF_SEM_PF)
+        for (int j = 0; j < cnt[0] + cnt[1]; ++j) d.smax_sc = fmaxf(d.smax_sc, A[4 * j + 3]);
     d.tabA = (const float4*)block;
     d.tabB = n > 0 ? (const float4*)((char*)block + bytesA) : nullptr;
     d.obs64 = n > 0 ? (const double*)((char*)block + 2 * bytesA) : nullptr;

@@ -33,6 +33,13 @@ __device__ __forceinline__ float dist2(float dx, float dy, float dz) {
     return fmaf(dz, dz, fmaf(dy, dy, __fmul_rn(dx, dx)));
 }
 
+// Pruning bound for the sphere / cube distance (see eval_static_chunk): candidates with
+// d^2 >= bound cannot lower `best`.  best = inf -> bound = inf (nothing is pruned).
+__device__ __forceinline__ float prune_bound(float best, float smax) {
+    const float t = __fadd_rn(best, smax);
+    return __fmul_rn(__fmul_rn(t, t), 1.00000095367431640625f);  // 1 + 2^-20
+}
+
 // Static analytic obstacles, table rows [lo, hi) of the staged chunk whose first row has global
 // index `base`.  Kind buckets are global index ranges (tables are kind-sorted).
 template <int SEM, int NP>
@@ -52,38 +59,15 @@ __device__ __forceinline__ void eval_static_chunk(const EnvDev& e, const Tables&
             }
         }
     } else if constexpr (SEM == TF_SEM_PF) {
+        // chunk-local row ranges of each kind (tables are kind-sorted: spheres, cubes, cylinders, aabbs)
         const int s_end = e.n_sphere, c_end = s_end + e.n_cube, y_end = c_end + e.n_cyl;
-        int k = 0;
-        // spheres PF:37-39, PF:54-55
-        int lim = min(cnt, max(0, s_end - base));
+        const int s_hi = min(cnt, max(0, s_end - base));
+        const int c_hi = min(cnt, max(0, c_end - base));
+        const int y_hi = min(cnt, max(0, y_end - base));
+        // cylinders first PF:40-42 (AABB s,s,2s), PF:56-57 (z-only distance): they are cheap and pull
+        // `best` down early, which makes the pruning below bite (min / or are order-independent)
 #pragma unroll 2
-        for (; k < lim; ++k) {
-            const float4 o = t.A[k];
-            const float s2 = __fmul_rn(o.w, o.w);
-#pragma unroll
-            for (int s = 0; s < NP; ++s) {
-                float d2 = dist2(x[s] - o.x, y[s] - o.y, z[s] - o.z);
-                hit |= (d2 <= s2) ? (1u << s) : 0u;
-                best[s] = fminf(best[s], fmaxf(0.0f, __fsub_rn(__fsqrt_rn(d2), o.w)));
-            }
-        }
-        // cubes PF:34-36 (Chebyshev collision), PF:52-53 (spherical distance)
-        lim = min(cnt, max(0, c_end - base));
-#pragma unroll 2
-        for (; k < lim; ++k) {
-            const float4 o = t.A[k];
-#pragma unroll
-            for (int s = 0; s < NP; ++s) {
-                float dx = x[s] - o.x, dy = y[s] - o.y, dz = z[s] - o.z;
-                bool in = fabsf(dx) <= o.w && fabsf(dy) <= o.w && fabsf(dz) <= o.w;
-                hit |= in ? (1u << s) : 0u;
-                best[s] = fminf(best[s], fmaxf(0.0f, __fsub_rn(__fsqrt_rn(dist2(dx, dy, dz)), o.w)));
-            }
-        }
-        // cylinders PF:40-42 (AABB s,s,2s), PF:56-57 (z-only distance)
-        lim = min(cnt, max(0, y_end - base));
-#pragma unroll 2
-        for (; k < lim; ++k) {
+        for (int k = c_hi; k < y_hi; ++k) {
             const float4 o = t.A[k];
             const float h = __fmul_rn(2.0f, o.w);
 #pragma unroll
@@ -94,6 +78,45 @@ __device__ __forceinline__ void eval_static_chunk(const EnvDev& e, const Tables&
                 best[s] = fminf(best[s], fmaxf(0.0f, __fsub_rn(az, h)));
             }
         }
+        // Spheres and cubes share the distance max(0, ||p-c|| - s).  The sqrt is skipped whenever
+        // d^2 >= fl(fl(t*t) * (1 + 2^-20)), t = fl(best + s_max): then fl(sqrt(d^2) - s) >= best is
+        // guaranteed, so the minimum — and every bit of the result — is unchanged.
+        const float smax = e.smax_sc;
+        float bound[NP];
+#pragma unroll
+        for (int s = 0; s < NP; ++s) bound[s] = prune_bound(best[s], smax);
+        // spheres PF:37-39, PF:54-55
+#pragma unroll 2
+        for (int k = 0; k < s_hi; ++k) {
+            const float4 o = t.A[k];
+            const float s2 = __fmul_rn(o.w, o.w);
+#pragma unroll
+            for (int s = 0; s < NP; ++s) {
+                float d2 = dist2(x[s] - o.x, y[s] - o.y, z[s] - o.z);
+                hit |= (d2 <= s2) ? (1u << s) : 0u;
+                if (d2 < bound[s]) {
+                    best[s] = fminf(best[s], fmaxf(0.0f, __fsub_rn(__fsqrt_rn(d2), o.w)));
+                    bound[s] = prune_bound(best[s], smax);
+                }
+            }
+        }
+        // cubes PF:34-36 (Chebyshev collision), PF:52-53 (spherical distance)
+#pragma unroll 2
+        for (int k = s_hi; k < c_hi; ++k) {
+            const float4 o = t.A[k];
+#pragma unroll
+            for (int s = 0; s < NP; ++s) {
+                float dx = x[s] - o.x, dy = y[s] - o.y, dz = z[s] - o.z;
+                bool in = fabsf(dx) <= o.w && fabsf(dy) <= o.w && fabsf(dz) <= o.w;
+                hit |= in ? (1u << s) : 0u;
+                float d2 = dist2(dx, dy, dz);
+                if (d2 < bound[s]) {
+                    best[s] = fminf(best[s], fmaxf(0.0f, __fsub_rn(__fsqrt_rn(d2), o.w)));
+                    bound[s] = prune_bound(best[s], smax);
+                }
+            }
+        }
+        int k = y_hi;
         // AABBs (extension): true box distance
         for (; k < cnt; ++k) {
             const float4 o = t.A[k];
