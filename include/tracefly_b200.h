@@ -239,6 +239,12 @@ int tf_replace_worst(float* pop_dev, float* fit_dev, const int32_t* worst_idx_de
                      const float* gathered_rows_dev, const float* gathered_fit_dev,
                      int world, int self_rank, int E, void* stream);
 
+/* ---- compact host format -------------------------------------------------- */
+/* int16[n][4] (x, y, z, pad) <-> f32[n][4]: lattice chromosomes at 8 B per waypoint for the PCIe leg.
+ * Packing rounds to nearest and saturates; it is exact for integer coordinates in [-32768, 32767]. */
+int tf_unpack_i16(const int16_t* in_dev, float* pop_dev, int64_t n_waypoints, void* stream);
+int tf_pack_i16(const float* pop_dev, int16_t* out_dev, int64_t n_waypoints, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------ */
 int tf_version(void);
 const char* tf_strerror(int status);

@@ -230,3 +230,34 @@ def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind):
             L.set_option(L.OPT_DISABLE_STREAM, 0)
     for a, b in zip(res[0], res[1]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("fmt", ["f32", "i16"])
+def test_host_stepper_round_trip(tf, fmt):
+    """Host-array API: pinned population in -> fitness + next population out equals the device API."""
+    torch, L, B = tf
+    P, W = 4099, 64
+    rng = np.random.default_rng(1)
+    table = random_table(rng, 60, 64, sem_pf=True)
+    env = B.Environment(L.SEM_PF, table, 0.0)
+    ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=4, mutation_rate=0.2)
+    prm = L.default_params(dist_zero_guard=0)
+    pops = [B.init_walks(s, P, W, start=(32, 32, 32), lo=(0, 0, 0), hi=(63, 63, 63)) for s in (1, 2, 3)]
+    stepper = B.HostStepper(env, P, W, ga, prm, fmt=fmt, depth=2)
+    hdt = torch.float32 if fmt == "f32" else torch.int16
+    hosts = [p.to(hdt).cpu().pin_memory() for p in pops]
+    tickets = [stepper.submit(hosts[0], seed=5, generation=0), stepper.submit(hosts[1], seed=5, generation=1)]
+    got = []
+    for i in range(3):
+        fit_h, next_h = stepper.result(tickets.pop(0))
+        got.append((fit_h.clone(), next_h.clone()))
+        if i == 0:
+            tickets.append(stepper.submit(hosts[2], seed=5, generation=2))
+    for g, (pop, (fit_h, next_h)) in enumerate(zip(pops, got)):
+        fit, _ = B.fitness_batch(pop, None, env, prm)
+        top = B.rank_topk(fit, 2)
+        nxt, nfit, *_ = B.generation(env, pop, fit, top, ga, prm, seed=5, generation=g)
+        assert torch.equal(fit.cpu(), fit_h)
+        assert torch.equal(nxt.to(hdt).cpu(), next_h)
+    h2d, d2h = stepper.bytes_per_step()
+    assert h2d == P * W * 4 * (4 if fmt == "f32" else 2)

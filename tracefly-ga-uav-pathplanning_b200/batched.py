@@ -389,3 +389,76 @@ def evolve_batch(pop, env, generations, ga=None, params=None, seed=0, tapes=None
     if tracker is not None:
         out.update(best_path=tracker.best_path, best_fit=tracker.best_fit, best_gen=tracker.best_gen)
     return out
+
+
+# ------------------------------------------------------------------------------------ host round trips
+class HostStepper:
+    """The array API for callers whose populations live in HOST memory (what a drop-in call from
+    the reference's process looks like): each `submit` copies a pinned host population to the GPU,
+    runs fitness -> rank -> fused generation there, and copies the fitness vector and the next
+    population back.  `depth` requests are in flight on separate streams, so the D2H leg of step n
+    overlaps the H2D leg of step n+1 (PCIe is full duplex).  fmt="i16" moves lattice chromosomes as
+    int16[P, W, 4] (8 B per waypoint) and converts on the device (tf_unpack_i16 / tf_pack_i16)."""
+
+    def __init__(self, env, P, W, ga=None, params=None, fmt="f32", depth=2, device="cuda"):
+        _require_cuda()
+        if fmt not in ("f32", "i16"):
+            raise ValueError("fmt must be 'f32' or 'i16'")
+        self.env, self.P, self.W, self.fmt = env, P, W, fmt
+        self.ga = ga or L.default_ga_params()
+        self.params = params or L.default_params(dist_zero_guard=1 if env.semantics != L.SEM_PF else 0)
+        k = max(min(self.ga.n_elite, P), min(self.ga.n_top, P) if self.ga.selection == L.SEL_TRUNCATION else 1, 1)
+        hdt = torch.float32 if fmt == "f32" else torch.int16
+        self.slots = []
+        for _ in range(depth):
+            s = dict(stream=torch.cuda.Stream(), pop=torch.empty((P, W, 4), dtype=torch.float32, device=device),
+                     nxt=torch.empty((P, W, 4), dtype=torch.float32, device=device),
+                     fit=torch.empty(P, dtype=torch.float32, device=device),
+                     nfit=torch.empty(P, dtype=torch.float32, device=device),
+                     top=torch.empty(k, dtype=torch.int32, device=device), topk=TopK(P, k, device=device),
+                     host_fit=torch.empty(P, dtype=torch.float32).pin_memory(),
+                     host_next=torch.empty((P, W, 4), dtype=hdt).pin_memory(), busy=False)
+            if fmt == "i16":
+                s["stage_in"] = torch.empty((P, W, 4), dtype=torch.int16, device=device)
+                s["stage_out"] = torch.empty((P, W, 4), dtype=torch.int16, device=device)
+            self.slots.append(s)
+        self._n = 0
+
+    def bytes_per_step(self):
+        e = 4 if self.fmt == "f32" else 2
+        return self.P * self.W * 4 * e, self.P * self.W * 4 * e + self.P * 4
+
+    def submit(self, host_pop, seed=0, generation=0):
+        """host_pop: pinned CPU tensor [P, W, 4] (float32, or int16 when fmt='i16').  Returns a ticket."""
+        s = self.slots[self._n % len(self.slots)]
+        if s["busy"]:
+            raise RuntimeError("HostStepper: collect the oldest result before submitting more work")
+        n4 = self.P * self.W
+        with torch.cuda.stream(s["stream"]):
+            if self.fmt == "f32":
+                s["pop"].copy_(host_pop, non_blocking=True)
+            else:
+                s["stage_in"].copy_(host_pop, non_blocking=True)
+                check(lib.tf_unpack_i16(_ptr(s["stage_in"]), _ptr(s["pop"]), n4, _stream()), "tf_unpack_i16")
+            fitness_batch(s["pop"], None, self.env, self.params, out=s["fit"], want_collisions=False)
+            s["topk"](s["fit"], out=s["top"])
+            check(lib.tf_generation(self.env.handle, _ptr(s["pop"]), _ptr(s["fit"]), _ptr(s["top"]), None, seed,
+                                    generation, C.byref(self.ga), C.byref(self.params), self.P, self.W, _ptr(s["nxt"]),
+                                    _ptr(s["nfit"]), None, None, None, _stream()), "tf_generation")
+            s["host_fit"].copy_(s["fit"], non_blocking=True)
+            if self.fmt == "f32":
+                s["host_next"].copy_(s["nxt"], non_blocking=True)
+            else:
+                check(lib.tf_pack_i16(_ptr(s["nxt"]), _ptr(s["stage_out"]), n4, _stream()), "tf_pack_i16")
+                s["host_next"].copy_(s["stage_out"], non_blocking=True)
+        s["busy"] = True
+        self._n += 1
+        return self._n - 1
+
+    def result(self, ticket):
+        """Blocks until that request's D2H copies have landed.  -> (fitness f32[P], next population) pinned
+        host tensors owned by the stepper (valid until the slot is reused `depth` submits later)."""
+        s = self.slots[ticket % len(self.slots)]
+        s["stream"].synchronize()
+        s["busy"] = False
+        return s["host_fit"], s["host_next"]

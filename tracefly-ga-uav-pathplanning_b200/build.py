@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libtracefly_b200.so")
-SOURCES = ["tf_env.cu", "tf_fitness.cu", "tf_rank.cu", "tf_ga.cu"]
-HEADERS = ["tf_common.cuh", "tf_fitness_dev.cuh", "tf_ga_dev.cuh", "../../include/tracefly_b200.h"]
+SOURCES = ["tf_env.cu", "tf_fitness.cu", "tf_rank.cu", "tf_ga.cu", "tf_io.cu"]
+HEADERS = ["tf_common.cuh", "tf_fitness_dev.cuh", "tf_ga_dev.cuh", "tf_stream_dev.cuh", "../../include/tracefly_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
