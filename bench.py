@@ -157,6 +157,7 @@ def build_gpu_workload(cfg, rank, torch, B, L):
         params.hazard_weight = 0.5
     if cfg["n_dyn"]:
         env.set_dynamic(dyn_table(cfg, cfg["n_dyn"], SEED), 2.0)
+        env.build_dynamic_index(W, (0, 0, 0), cfg["world"], cell=float(os.environ.get("TF_DYN_CELL", 32)), cap=int(os.environ.get("TF_DYN_CAP", 48)), band=int(os.environ.get("TF_DYN_BAND", 16)))
     g = torch.Generator(device="cuda")
     g.manual_seed(SEED + 100 + rank)
     if cfg["n_analytic"]:

@@ -84,10 +84,20 @@ int tf_env_create(int semantics, const tf_obstacle* obs_host, int n, float safet
  * reference-order kernels then see positions / sizes / safety radius unrounded. */
 int tf_env_create_f64(int semantics, const double* obs64_host, int n, double safety_radius, tf_env** out);
 int tf_env_set_dynamic(tf_env* env, const tf_dyn_obstacle* dyn_host, int n, float safety_radius);
+/* Optional acceleration of the moving spheres: a uniform grid over [box_lo, box_hi) with `cell`-sized
+ * cells, one copy per band of `band` consecutive integer times, whose entries list (up to `cap`) the
+ * spheres that can be nearest to, or collide with, a point of the cell at a time of the band
+ * (t < time_slices).  Results are bit-identical to the brute-force loop; points outside the box,
+ * fractional times and overflowed cells fall back to it. */
+int tf_env_build_dynamic_index(tf_env* env, int time_slices, int band, const float box_lo[3],
+                               const float box_hi[3], float cell, int cap, void* stream);
+/* Diagnostics of the index: number of lists, overflowed lists, mean / max list length. */
+int tf_env_dynamic_index_stats(const tf_env* env, int64_t* n_lists, int64_t* n_overflow, double* mean_len, int* max_len);
 /* Bit-packed occupancy grid in BRICK layout (see tf_voxel_*): caller-owned device memory,
  * must stay alive while the env uses it.  nx, ny, nz multiples of 8.  NULL detaches. */
 int tf_env_set_voxels(tf_env* env, const uint32_t* bricks_dev, int nx, int ny, int nz);
-/* Hazard heat-map f32[nt][ny][nx] (caller-owned device memory).  A waypoint i at (x, y)
+/* Hazard heat-map f32[nt][ny][nx] on the device; the env keeps its own (transposed) copy, so the
+ * caller's buffer may be released after the call.  A waypoint i at (x, y)
  * samples tri-linearly at gx = x*sx + ox, gy = y*sy + oy, gt = i*st (clamped).  NULL detaches. */
 int tf_env_set_hazard(tf_env* env, const float* hazard_dev, int nt, int ny, int nx,
                       float sx, float sy, float ox, float oy, float st);
@@ -254,7 +264,7 @@ int tf_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_byt
 void tf_philox4x32_10(uint32_t key0, uint32_t key1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                       uint32_t out[4]);
 /* Options.  TF_OPT_DISABLE_STREAM = 1 forces the LSU-path kernels even where the TMA-staged
- * kernels apply (W = 32 / 64 / 128, fixed length); both give bit-identical results. */
+ * kernels apply (W = 32 / 64, fixed length); both give bit-identical results. */
 #define TF_OPT_DISABLE_STREAM 1
 int tf_set_option(int option, int value);
 /* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */

@@ -171,3 +171,35 @@ def test_error_behaviour(tf):
         B.Environment(7, None, 0.0)
     fit, coll = B.fitness_batch(torch.zeros((0, 8, 4), device="cuda"), None, env)
     assert fit.numel() == 0
+
+
+def test_dynamic_index_equals_brute_force(tf):
+    """tf_env_build_dynamic_index: bit-identical fitness / flags, with points inside and outside the
+    index box, integer and fractional (sampled) times, and a cell capacity small enough to overflow."""
+    torch, L, B = tf
+    rng = np.random.default_rng(21)
+    P, W, n = 3000, 64, 700
+    world = 256
+    dyn = np.zeros((n, 8), np.float32)
+    dyn[:, :3] = rng.uniform(0, world, size=(n, 3))
+    dyn[:, 3] = rng.integers(1, 5, size=n)
+    dyn[:, 4:7] = rng.uniform(-1, 1, size=(n, 3))
+    pop_h = O.init_walks(13, P, W, (128, 128, 128), (-20, -20, -20), (world + 20, world + 20, world + 20),
+                         start_pp=np.concatenate([rng.uniform(-10, world + 10, size=(P, 3)).astype(np.float32).round(),
+                                                  np.zeros((P, 1), np.float32)], axis=1))
+    pop = torch.from_numpy(pop_h).cuda()
+    oe = O.OracleEnv(O.SEM_NONE, None, 0.0, dyn=dyn, dyn_safety=2.0)
+    for S in (1, 2):
+        prm = L.default_params(samples_per_segment=S)
+        ofit, ocoll = None, None
+        for cap, band in ((0, 1), (64, 1), (3, 1), (128, 16), (256, 64)):
+            env = B.Environment.empty().set_dynamic(dyn, 2.0)
+            if cap:
+                env.build_dynamic_index(W, (0, 0, 0), (world, world, world), cell=32.0, cap=cap, band=band)
+            fit, coll = B.fitness_batch(pop, None, env, prm)
+            if ofit is None:
+                O.set_threads(8)
+                ofit, ocoll = O.fitness_f32(oe, pop_h, None, O.default_params(guard=1, samples=S))
+                O.set_threads(1)
+            assert np.array_equal(ocoll, as_u32(coll)), (S, cap, band)
+            assert np.array_equal(ofit, fit.cpu().numpy()), (S, cap, band)

@@ -88,6 +88,76 @@ __global__ void pack_linear_kernel(const uint32_t* __restrict__ lin, uint32_t* _
     bricks[i] = out;
 }
 
+// Candidate index of the moving spheres.  One CTA per (time band, cell); a band covers `band`
+// consecutive integer times.  With m the cell centre, rho its half diagonal and dmin_t the distance
+// from m to the nearest sphere centre at time t, every sphere that can be NEAREST to some point of
+// the cell at time t has |m - c(t)| <= dmin_t + 2 rho, and every sphere that can COLLIDE with one
+// has |m - c(t)| <= R + rho.  A sphere is listed if either holds for any t of the band.  Both tests
+// carry a relative 1e-5 and an absolute 1e-3 margin for the float rounding of the cell assignment.
+constexpr int kIdxThreads = 128;
+constexpr int kIdxMaxPerThread = 16;  // n_dyn <= 2048
+__global__ void __launch_bounds__(kIdxThreads)
+build_dyn_index_kernel(const float4* __restrict__ dynA, const float4* __restrict__ dynB, int n, int T, int band, int gx,
+                       int gy, int gz, float ox, float oy, float oz, float h, int cap, int32_t* __restrict__ cand,
+                       int32_t* __restrict__ count) {
+    __shared__ float red[kIdxThreads];
+    __shared__ int n_list;
+    const size_t ncell = (size_t)gx * gy * gz;
+    const size_t cellid = blockIdx.x;
+    const int tb = (int)(cellid / ncell);
+    const size_t c = cellid % ncell;
+    const int ix = (int)(c % gx), iy = (int)((c / gx) % gy), iz = (int)(c / ((size_t)gx * gy));
+    const float mx = ox + ((float)ix + 0.5f) * h, my = oy + ((float)iy + 0.5f) * h, mz = oz + ((float)iz + 0.5f) * h;
+    const float rho = 0.8660254f * h * 1.00001f + 1e-3f;
+    uint32_t marked = 0;  // bit j: sphere threadIdx.x + j * kIdxThreads is a candidate
+    if (threadIdx.x == 0) n_list = 0;
+    for (int t = tb * band; t < min(T, (tb + 1) * band); ++t) {
+        const float tm = (float)t;
+        float dmin = INFINITY;
+        for (int k = threadIdx.x; k < n; k += kIdxThreads) {
+            const float4 o = dynA[k], v = dynB[k];
+            const float dx = mx - fmaf(v.x, tm, o.x), dy = my - fmaf(v.y, tm, o.y), dz = mz - fmaf(v.z, tm, o.z);
+            dmin = fminf(dmin, sqrtf(dx * dx + dy * dy + dz * dz));
+        }
+        __syncthreads();
+        red[threadIdx.x] = dmin;
+        __syncthreads();
+        for (int off = kIdxThreads / 2; off > 0; off >>= 1) {
+            if (threadIdx.x < off) red[threadIdx.x] = fminf(red[threadIdx.x], red[threadIdx.x + off]);
+            __syncthreads();
+        }
+        const float near_lim = (red[0] + 2.0f * rho) * 1.00001f + 1e-3f;
+        int j = 0;
+        for (int k = threadIdx.x; k < n; k += kIdxThreads, ++j) {
+            const float4 o = dynA[k], v = dynB[k];
+            const float dx = mx - fmaf(v.x, tm, o.x), dy = my - fmaf(v.y, tm, o.y), dz = mz - fmaf(v.z, tm, o.z);
+            const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+            const float coll_lim = (sqrtf(o.w) + rho) * 1.00001f + 1e-3f;
+            if (d <= near_lim || d <= coll_lim) marked |= 1u << j;
+        }
+    }
+    __syncthreads();
+    int j = 0;
+    for (int k = threadIdx.x; k < n; k += kIdxThreads, ++j) {
+        if ((marked >> j) & 1u) {
+            const int pos = atomicAdd(&n_list, 1);
+            if (pos < cap) cand[cellid * cap + pos] = k;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) count[cellid] = n_list <= cap ? n_list : -1;
+}
+
+// [t][y][x] -> [y][x][t]
+__global__ void hazard_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int nt, size_t nyx) {
+    const size_t n = nyx * (size_t)nt;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = i / nt;
+        const int t = (int)(i - c * nt);
+        out[i] = in[(size_t)t * nyx + c];
+    }
+}
+
 }  // namespace tf
 
 using namespace tf;
@@ -182,7 +252,9 @@ extern "C" int tf_env_set_dynamic(tf_env* env, const tf_dyn_obstacle* dyn_host, 
     if (!env || n < 0 || (n > 0 && !dyn_host)) return TF_ERR_INVALID;
     if (n > 2048) return TF_ERR_SHAPE;
     if (env->dyn_block) { cudaFree(env->dyn_block); env->dyn_block = nullptr; }
-    env->d.n_dyn = 0; env->d.dynA = env->d.dynB = nullptr;
+    env->d.n_dyn = env->d.n_dyn_smem = 0; env->d.dynA = env->d.dynB = nullptr;
+    if (env->dindex_block) { cudaFree(env->dindex_block); env->dindex_block = nullptr; }
+    env->d.dcand = env->d.dcount = nullptr;
     if (n == 0) return TF_OK;
     std::vector<float> A((size_t)n * 4), B((size_t)n * 4);
     for (int i = 0; i < n; ++i) {
@@ -195,9 +267,65 @@ extern "C" int tf_env_set_dynamic(tf_env* env, const tf_dyn_obstacle* dyn_host, 
     TF_CUDA(cudaMalloc(&env->dyn_block, (size_t)n * 32));
     TF_CUDA(cudaMemcpy(env->dyn_block, A.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
     TF_CUDA(cudaMemcpy((char*)env->dyn_block + (size_t)n * 16, B.data(), (size_t)n * 16, cudaMemcpyHostToDevice));
-    env->d.n_dyn = n;
+    env->d.n_dyn = env->d.n_dyn_smem = n;
     env->d.dynA = (const float4*)env->dyn_block;
     env->d.dynB = (const float4*)((char*)env->dyn_block + (size_t)n * 16);
+    return TF_OK;
+}
+
+extern "C" int tf_env_build_dynamic_index(tf_env* env, int time_slices, int band, const float box_lo[3],
+                                          const float box_hi[3], float cell, int cap, void* stream) {
+    if (!env || !box_lo || !box_hi) return TF_ERR_INVALID;
+    if (env->d.n_dyn <= 0) return TF_ERR_INVALID;
+    if (time_slices < 1 || time_slices > 4096 || band < 1 || cell <= 0.0f || cap < 1 || cap > 1024) return TF_ERR_SHAPE;
+    if (env->d.n_dyn > kIdxThreads * kIdxMaxPerThread) return TF_ERR_SHAPE;
+    const int nbands = (time_slices + band - 1) / band;
+    int g[3];
+    for (int a = 0; a < 3; ++a) {
+        if (!(box_hi[a] > box_lo[a])) return TF_ERR_SHAPE;
+        g[a] = (int)ceilf((box_hi[a] - box_lo[a]) / cell);
+        if (g[a] < 1 || g[a] > 256) return TF_ERR_SHAPE;
+    }
+    const size_t ncell = (size_t)g[0] * g[1] * g[2];
+    const size_t nlist = ncell * (size_t)nbands;
+    if (nlist > (size_t)1 << 26) return TF_ERR_SHAPE;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    if (env->dindex_block) { cudaFree(env->dindex_block); env->dindex_block = nullptr; }
+    env->d.dcand = env->d.dcount = nullptr;
+    const size_t bytes_count = ((nlist * 4 + 255) / 256) * 256, bytes_cand = nlist * (size_t)cap * 4;
+    TF_CUDA(cudaMalloc(&env->dindex_block, bytes_count + bytes_cand));
+    int32_t* count = (int32_t*)env->dindex_block;
+    int32_t* cand = (int32_t*)((char*)env->dindex_block + bytes_count);
+    build_dyn_index_kernel<<<(unsigned)nlist, kIdxThreads, 0, (cudaStream_t)stream>>>(
+        env->d.dynA, env->d.dynB, env->d.n_dyn, time_slices, band, g[0], g[1], g[2], box_lo[0], box_lo[1], box_lo[2], cell,
+        cap, cand, count);
+    TF_LAUNCH_CHECK();
+    TF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    env->d.dcand = cand; env->d.dcount = count;
+    env->d.dT = time_slices; env->d.dband = band; env->d.dgx = g[0]; env->d.dgy = g[1]; env->d.dgz = g[2]; env->d.dcap = cap;
+    env->d.dox = box_lo[0]; env->d.doy = box_lo[1]; env->d.doz = box_lo[2]; env->d.dinv_h = 1.0f / cell;
+    env->d.n_dyn_smem = 0;  // the kernels read the records through L1 / L2 now
+    return TF_OK;
+}
+
+extern "C" int tf_env_dynamic_index_stats(const tf_env* env, int64_t* n_lists, int64_t* n_overflow, double* mean_len,
+                                          int* max_len) {
+    if (!env || !env->d.dcount) return TF_ERR_INVALID;
+    const size_t n = (size_t)((env->d.dT + env->d.dband - 1) / env->d.dband) * env->d.dgx * env->d.dgy * env->d.dgz;
+    std::vector<int32_t> h(n);
+    TF_CUDA(cudaMemcpy(h.data(), env->d.dcount, n * 4, cudaMemcpyDeviceToHost));
+    int64_t over = 0;
+    double sum = 0.0;
+    int mx = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (h[i] < 0) ++over;
+        else { sum += h[i]; if (h[i] > mx) mx = h[i]; }
+    }
+    if (n_lists) *n_lists = (int64_t)n;
+    if (n_overflow) *n_overflow = over;
+    if (mean_len) *mean_len = n > (size_t)over ? sum / (double)(n - over) : 0.0;
+    if (max_len) *max_len = mx;
     return TF_OK;
 }
 
@@ -214,9 +342,19 @@ extern "C" int tf_env_set_voxels(tf_env* env, const uint32_t* bricks_dev, int nx
 extern "C" int tf_env_set_hazard(tf_env* env, const float* hazard_dev, int nt, int ny, int nx, float sx, float sy,
                                  float ox, float oy, float st) {
     if (!env) return TF_ERR_INVALID;
+    if (env->hazard_block) { cudaFree(env->hazard_block); env->hazard_block = nullptr; }
     if (!hazard_dev) { env->d.hazard = nullptr; return TF_OK; }
     if (nt <= 0 || ny <= 0 || nx <= 0) return TF_ERR_SHAPE;
-    env->d.hazard = hazard_dev;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    // the env owns a transposed copy [y][x][t] (see hazard_sample); the caller's tensor is not kept
+    const size_t n = (size_t)nt * ny * nx;
+    TF_CUDA(cudaMalloc(&env->hazard_block, n * 4));
+    hazard_transpose_kernel<<<(unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256>>>(
+        hazard_dev, (float*)env->hazard_block, nt, (size_t)ny * nx);
+    TF_LAUNCH_CHECK();
+    TF_CUDA(cudaDeviceSynchronize());
+    env->d.hazard = (const float*)env->hazard_block;
     env->d.nt = nt; env->d.hny = ny; env->d.hnx = nx;
     env->d.sx = sx; env->d.sy = sy; env->d.ox = ox; env->d.oy = oy; env->d.st = st;
     return TF_OK;
@@ -226,6 +364,8 @@ extern "C" int tf_env_destroy(tf_env* env) {
     if (!env) return TF_OK;
     if (env->dev_block) cudaFree(env->dev_block);
     if (env->dyn_block) cudaFree(env->dyn_block);
+    if (env->dindex_block) cudaFree(env->dindex_block);
+    if (env->hazard_block) cudaFree(env->hazard_block);
     free(env);
     return TF_OK;
 }

@@ -10,7 +10,7 @@ namespace tf {
 // memory with one TMA bulk copy; each of its 8 warps then takes TILES of 32 chromosomes:
 // phase B streams one chromosome at a time (coalesced float4 loads, L1 no-allocate, next
 // chromosome prefetched) and reduces it across the warp, phase C scores 32 chromosomes at once.
-template <int NW, int SEM, bool VOX, bool EXTRA>
+template <int NW, int SEM, bool VOX, int XF>
 __global__ void __launch_bounds__(kBlockThreads)
 fitness_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
                const float4* __restrict__ pop, const int32_t* __restrict__ lens, int P, int W, int T,
@@ -21,7 +21,7 @@ fitness_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_para
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwords = (W + 31) >> 5;
     const int nchunks = (SEM == TF_SEM_NONE) ? 0 : (e.n + kTableCap - 1) / kTableCap;
-    const bool need_stage = (SEM != TF_SEM_NONE && e.n > 0) || (EXTRA && e.n_dyn > 0);
+    const bool need_stage = (SEM != TF_SEM_NONE && e.n > 0) || (XF >= 1 && e.n_dyn_smem > 0);
     uint32_t phase = 0;
     bool first_chunk_resident = false;
 
@@ -32,7 +32,7 @@ fitness_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_para
         }
         __syncthreads();
         if (threadIdx.x == 0)
-            stage_chunk(e, sm.A, sm.B, 0, min(e.n, kTableCap), sm.bar, EXTRA && e.n_dyn > 0, sm.dA, sm.dB);
+            stage_chunk(e, sm.A, sm.B, 0, min(e.n, kTableCap), sm.bar, XF >= 1 && e.n_dyn_smem > 0, sm.dA, sm.dB);
         mbar_wait(sm.bar, phase);
         phase ^= 1;
         first_chunk_resident = true;
@@ -87,14 +87,14 @@ fitness_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_para
                     }
                 }
             }
-            reduce_chromosome<NW, SEM, VOX, EXTRA>(e, prm, tabs, cur, Lc, acc, c, sums);
+            reduce_chromosome<NW, SEM, VOX, XF>(e, prm, tabs, cur, Lc, acc, c, sums);
             cur = nxt;
             Lc = Ln;
         }
         // phase C: lane = chromosome
         if (lane < cnt) {
             const int p = p0 + lane;
-            fit[p] = combine_fitness<NW, EXTRA>(e, prm, sums);
+            fit[p] = combine_fitness<NW, XF>(e, prm, sums);
             if (coll) {
 #pragma unroll
                 for (int s = 0; s < NW; ++s)
@@ -104,10 +104,10 @@ fitness_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_para
     }
 }
 
-template <int NW, int SEM, bool VOX, bool EXTRA>
+template <int NW, int SEM, bool VOX, int XF>
 static int launch_fitness(const EnvDev& e, const tf_params& prm, const float* pop, const int32_t* lens, int P, int W,
                           float* fit, uint32_t* coll, cudaStream_t st) {
-    auto kern = fitness_kernel<NW, SEM, VOX, EXTRA>;
+    auto kern = fitness_kernel<NW, SEM, VOX, XF>;
     size_t smem = smem_bytes_for(e);
     if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int T = tile_size_for(P);
@@ -122,11 +122,15 @@ template <int NW, int SEM>
 static int dispatch_flags(const EnvDev& e, const tf_params& prm, const float* pop, const int32_t* lens, int P, int W,
                           float* fit, uint32_t* coll, cudaStream_t st) {
     const bool vox = e.bricks != nullptr;
-    const bool extra = e.n_dyn > 0 || e.hazard != nullptr || prm.samples_per_segment > 1;
-    if (vox && extra) return launch_fitness<NW, SEM, true, true>(e, prm, pop, lens, P, W, fit, coll, st);
-    if (vox) return launch_fitness<NW, SEM, true, false>(e, prm, pop, lens, P, W, fit, coll, st);
-    if (extra) return launch_fitness<NW, SEM, false, true>(e, prm, pop, lens, P, W, fit, coll, st);
-    return launch_fitness<NW, SEM, false, false>(e, prm, pop, lens, P, W, fit, coll, st);
+    const int xf = prm.samples_per_segment > 1 ? 2 : ((e.n_dyn > 0 || e.hazard != nullptr) ? 1 : 0);
+    if (vox) {
+        if (xf == 2) return launch_fitness<NW, SEM, true, 2>(e, prm, pop, lens, P, W, fit, coll, st);
+        if (xf == 1) return launch_fitness<NW, SEM, true, 1>(e, prm, pop, lens, P, W, fit, coll, st);
+        return launch_fitness<NW, SEM, true, 0>(e, prm, pop, lens, P, W, fit, coll, st);
+    }
+    if (xf == 2) return launch_fitness<NW, SEM, false, 2>(e, prm, pop, lens, P, W, fit, coll, st);
+    if (xf == 1) return launch_fitness<NW, SEM, false, 1>(e, prm, pop, lens, P, W, fit, coll, st);
+    return launch_fitness<NW, SEM, false, 0>(e, prm, pop, lens, P, W, fit, coll, st);
 }
 
 template <int NW>

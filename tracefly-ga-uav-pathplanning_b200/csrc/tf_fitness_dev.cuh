@@ -135,20 +135,67 @@ __device__ __forceinline__ void eval_static_chunk(const EnvDev& e, const Tables&
 }
 
 // Moving spheres (extension): HR rules at c(t) = c0 + v t.  Returns min d^2 per point.
+// With a candidate index (tf_env_build_dynamic_index) a point at an integer time slice inside the
+// index box only visits the spheres listed for its cell — a superset of "nearest" and of "colliding"
+// by construction, so min / or (and every bit of the result) equal the brute-force loop.
+__device__ __forceinline__ void dyn_test(const float4 o, const float4 v, float x, float y, float z, float tm,
+                                         bool& hit, float& m2) {
+    const float cx = fmaf(v.x, tm, o.x), cy = fmaf(v.y, tm, o.y), cz = fmaf(v.z, tm, o.z);
+    const float d2 = dist2(x - cx, y - cy, z - cz);
+    hit = hit || (d2 <= o.w);
+    m2 = fminf(m2, d2);
+}
+
 template <int NP>
 __device__ __forceinline__ void eval_dynamic(const EnvDev& e, const Tables& t, const float (&x)[NP],
                                              const float (&y)[NP], const float (&z)[NP], const float (&tm)[NP],
                                              uint32_t& hit, float (&m2)[NP]) {
-    for (int k = 0; k < e.n_dyn; ++k) {
-        const float4 o = t.dA[k];
-        const float4 v = t.dB[k];
+    if (e.dcand == nullptr) {  // records staged in shared memory: brute force, all slots per record
+        for (int k = 0; k < e.n_dyn; ++k) {
+            const float4 o = t.dA[k];
+            const float4 v = t.dB[k];
 #pragma unroll
-        for (int s = 0; s < NP; ++s) {
-            float cx = fmaf(v.x, tm[s], o.x), cy = fmaf(v.y, tm[s], o.y), cz = fmaf(v.z, tm[s], o.z);
-            float d2 = dist2(x[s] - cx, y[s] - cy, z[s] - cz);
-            hit |= (d2 <= o.w) ? (1u << s) : 0u;
-            m2[s] = fminf(m2[s], d2);
+            for (int s = 0; s < NP; ++s) {
+                bool h = false;
+                dyn_test(o, v, x[s], y[s], z[s], tm[s], h, m2[s]);
+                hit |= h ? (1u << s) : 0u;
+            }
         }
+        return;
+    }
+#pragma unroll
+    for (int s = 0; s < NP; ++s) {
+        const int ti = (int)tm[s];
+        const int ix = __float2int_rd((x[s] - e.dox) * e.dinv_h), iy = __float2int_rd((y[s] - e.doy) * e.dinv_h),
+                  iz = __float2int_rd((z[s] - e.doz) * e.dinv_h);
+        const bool indexed = (float)ti == tm[s] && ti >= 0 && ti < e.dT && (unsigned)ix < (unsigned)e.dgx &&
+                             (unsigned)iy < (unsigned)e.dgy && (unsigned)iz < (unsigned)e.dgz;
+        int cnt = -1;
+        size_t cell = 0;
+        if (indexed) {
+            cell = ((size_t)(ti / e.dband) * e.dgz + iz) * e.dgy * e.dgx + (size_t)iy * e.dgx + ix;
+            cnt = __ldg(e.dcount + cell);
+        }
+        bool h = false;
+        if (cnt >= 0) {
+            const int32_t* list = e.dcand + cell * e.dcap;
+            int j = 0;
+            for (; j + 2 <= cnt; j += 2) {  // 2 ids, then 4 independent record loads in flight
+                const int i0 = __ldg(list + j), i1 = __ldg(list + j + 1);
+                const float4 a0 = __ldg(e.dynA + i0), a1 = __ldg(e.dynA + i1);
+                const float4 b0 = __ldg(e.dynB + i0), b1 = __ldg(e.dynB + i1);
+                dyn_test(a0, b0, x[s], y[s], z[s], tm[s], h, m2[s]);
+                dyn_test(a1, b1, x[s], y[s], z[s], tm[s], h, m2[s]);
+            }
+            for (; j < cnt; ++j) {
+                const int id = __ldg(list + j);
+                dyn_test(__ldg(e.dynA + id), __ldg(e.dynB + id), x[s], y[s], z[s], tm[s], h, m2[s]);
+            }
+        } else {  // outside the index (or an overflowed cell): every sphere, from global memory
+            for (int k = 0; k < e.n_dyn; ++k)
+                dyn_test(__ldg(e.dynA + k), __ldg(e.dynB + k), x[s], y[s], z[s], tm[s], h, m2[s]);
+        }
+        hit |= h ? (1u << s) : 0u;
     }
 }
 
@@ -191,12 +238,14 @@ __device__ __forceinline__ float hazard_sample(const EnvDev& e, float x, float y
     int x0 = (int)gx, y0 = (int)gy, t0 = (int)gt;
     int x1 = min(x0 + 1, e.hnx - 1), y1 = min(y0 + 1, e.hny - 1), t1 = min(t0 + 1, e.nt - 1);
     float fx = __fsub_rn(gx, (float)x0), fy = __fsub_rn(gy, (float)y0), ft = __fsub_rn(gt, (float)t0);
-    const float* h0 = e.hazard + (size_t)t0 * e.hny * e.hnx;
-    const float* h1 = e.hazard + (size_t)t1 * e.hny * e.hnx;
-    float v000 = __ldg(h0 + y0 * e.hnx + x0), v001 = __ldg(h0 + y0 * e.hnx + x1);
-    float v010 = __ldg(h0 + y1 * e.hnx + x0), v011 = __ldg(h0 + y1 * e.hnx + x1);
-    float v100 = __ldg(h1 + y0 * e.hnx + x0), v101 = __ldg(h1 + y0 * e.hnx + x1);
-    float v110 = __ldg(h1 + y1 * e.hnx + x0), v111 = __ldg(h1 + y1 * e.hnx + x1);
+    // the env keeps the map transposed to [y][x][t]: the lanes of a warp are consecutive waypoints, i.e.
+    // nearly the same (x, y) at consecutive times, so their taps fall into the same cache lines
+    const float* c00 = e.hazard + ((size_t)y0 * e.hnx + x0) * e.nt;
+    const float* c01 = e.hazard + ((size_t)y0 * e.hnx + x1) * e.nt;
+    const float* c10 = e.hazard + ((size_t)y1 * e.hnx + x0) * e.nt;
+    const float* c11 = e.hazard + ((size_t)y1 * e.hnx + x1) * e.nt;
+    float v000 = __ldg(c00 + t0), v001 = __ldg(c01 + t0), v010 = __ldg(c10 + t0), v011 = __ldg(c11 + t0);
+    float v100 = __ldg(c00 + t1), v101 = __ldg(c01 + t1), v110 = __ldg(c10 + t1), v111 = __ldg(c11 + t1);
     float a0 = lerp_f(lerp_f(v000, v001, fx), lerp_f(v010, v011, fx), fy);
     float a1 = lerp_f(lerp_f(v100, v101, fx), lerp_f(v110, v111, fx), fy);
     return lerp_f(a0, a1, ft);
@@ -204,7 +253,7 @@ __device__ __forceinline__ float hazard_sample(const EnvDev& e, float x, float y
 
 // Full collision / nearest-distance evaluation of ONE point against a fully staged table
 // (sample points of the S > 1 extension; requires a single chunk).
-template <int SEM, bool VOX, bool EXTRA>
+template <int SEM, bool VOX, int XF>
 __device__ __forceinline__ void eval_point_full(const EnvDev& e, const Tables& t, float x, float y, float z, float tm,
                                                 bool& hit_out, float& dnear) {
     float xs[1] = {x}, ys[1] = {y}, zs[1] = {z}, tms[1] = {tm};
@@ -212,7 +261,7 @@ __device__ __forceinline__ void eval_point_full(const EnvDev& e, const Tables& t
     float best[1] = {INFINITY};
     eval_static_chunk<SEM, 1>(e, t, 0, min(e.n, kTableCap), xs, ys, zs, hit, best);
     float dn = (SEM == TF_SEM_HR) ? __fsqrt_rn(best[0]) : best[0];
-    if constexpr (EXTRA) {
+    if constexpr (XF >= 1) {
         if (e.n_dyn > 0) {
             float m2[1] = {INFINITY};
             eval_dynamic<1>(e, t, xs, ys, zs, tms, hit, m2);
@@ -229,15 +278,15 @@ __device__ __forceinline__ void stage_chunk(const EnvDev& e, float4* sA, float4*
                                             uint64_t* bar, bool with_dyn, float4* sdA, float4* sdB) {
     // one elected thread arms the barrier with the byte count and issues the bulk copies
     uint32_t bytes = (uint32_t)cnt * 16u * (e.n_aabb > 0 ? 2u : 1u);
-    if (with_dyn) bytes += (uint32_t)e.n_dyn * 32u;
+    if (with_dyn) bytes += (uint32_t)e.n_dyn_smem * 32u;
     mbar_expect_tx(bar, bytes);
     if (cnt > 0) {
         tma_load_1d(sA, e.tabA + row0, (uint32_t)cnt * 16u, bar);
         if (e.n_aabb > 0) tma_load_1d(sB, e.tabB + row0, (uint32_t)cnt * 16u, bar);
     }
     if (with_dyn) {
-        tma_load_1d(sdA, e.dynA, (uint32_t)e.n_dyn * 16u, bar);
-        tma_load_1d(sdB, e.dynB, (uint32_t)e.n_dyn * 16u, bar);
+        tma_load_1d(sdA, e.dynA, (uint32_t)e.n_dyn_smem * 16u, bar);
+        tma_load_1d(sdB, e.dynB, (uint32_t)e.n_dyn_smem * 16u, bar);
     }
 }
 
@@ -247,7 +296,7 @@ struct SmemLayout {
 };
 __host__ __device__ inline size_t smem_bytes_for(const EnvDev& e) {
     size_t cap = (size_t)(e.n < kTableCap ? e.n : kTableCap);
-    return 16 + cap * 16 * (e.n_aabb > 0 ? 2 : 1) + (size_t)e.n_dyn * 32;
+    return 16 + cap * 16 * (e.n_aabb > 0 ? 2 : 1) + (size_t)e.n_dyn_smem * 32;
 }
 __device__ __forceinline__ SmemLayout carve_smem(const EnvDev& e, unsigned char* smem) {
     SmemLayout s;
@@ -257,7 +306,7 @@ __device__ __forceinline__ SmemLayout carve_smem(const EnvDev& e, unsigned char*
     s.B = s.A + (e.n_aabb > 0 ? cap : 0);
     s.dA = s.B + cap;
     if (e.n_aabb == 0) s.dA = s.A + cap;
-    s.dB = s.dA + e.n_dyn;
+    s.dB = s.dA + e.n_dyn_smem;
     return s;
 }
 
@@ -307,7 +356,7 @@ inline int tile_size_for(int P) {
 }
 
 // Phase B for one chromosome (all 32 lanes cooperate; `c` = its index in the tile).
-template <int NW, int SEM, bool VOX, bool EXTRA>
+template <int NW, int SEM, bool VOX, int XF>
 __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_params& prm, const Tables& t,
                                                   const Lanes<NW>& cur, int L, PointAcc<NW, SEM>& acc, int c,
                                                   TileSums<NW>& out) {
@@ -316,11 +365,11 @@ __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_para
     int turns = 0, ncoll = 0;
     uint32_t hit = acc.hit;
     // without any distance source d_near = inf and every proximity term is exactly 0 (HR:26-27)
-    const bool has_dist = (SEM != TF_SEM_NONE) || (EXTRA && e.n_dyn > 0);
+    const bool has_dist = (SEM != TF_SEM_NONE) || (XF >= 1 && e.n_dyn > 0);
     float dn[NW];
 #pragma unroll
     for (int s = 0; s < NW; ++s) dn[s] = (SEM == TF_SEM_HR) ? __fsqrt_rn(acc.best[s]) : acc.best[s];
-    if constexpr (EXTRA) {
+    if constexpr (XF >= 1) {
         if (e.n_dyn > 0) {
             float m2[NW], tm[NW];
 #pragma unroll
@@ -333,7 +382,7 @@ __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_para
             for (int s = 0; s < NW; ++s) dn[s] = fminf(dn[s], __fsqrt_rn(m2[s]));
         }
     }
-    const int S = EXTRA ? max(prm.samples_per_segment, 1) : 1;
+    const int S = (XF >= 2) ? max(prm.samples_per_segment, 1) : 1;
     // previous waypoint of each slot: rotate by one lane; lane 0 takes lane 31 of the previous slot
     float rx_prev = 0.f, ry_prev = 0.f, rz_prev = 0.f;
 #pragma unroll
@@ -353,7 +402,7 @@ __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_para
         if (lane == c) out.cw[s] = word;
         ncoll += h ? 1 : 0;
         if (has_dist && valid) a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[s])));  // HR:46
-        if constexpr (EXTRA) {
+        if constexpr (XF >= 1) {
             if (e.hazard != nullptr && valid) a_haz = __fadd_rn(a_haz, hazard_sample(e, cur.x[s], cur.y[s], (float)k));
         }
         if (valid && k >= 1) {
@@ -361,12 +410,12 @@ __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_para
             a_dist = __fadd_rn(a_dist, __fsqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
             a_alt = __fadd_rn(a_alt, fabsf(dz));                         // HR:44
             if (k <= L - 2) turns += (cur.x[s] != px || cur.y[s] != py) ? 1 : 0;  // HR:38-40,43
-            if constexpr (EXTRA) {
+            if constexpr (XF >= 2) {
                 for (int j = 1; j < S; ++j) {  // extension: samples inside segment (k-1, k)
                     float tj = __fdiv_rn((float)j, (float)S);
                     bool sh;
                     float sdn;
-                    eval_point_full<SEM, VOX, EXTRA>(e, t, fmaf(dx, tj, px), fmaf(dy, tj, py), fmaf(dz, tj, pz),
+                    eval_point_full<SEM, VOX, XF>(e, t, fmaf(dx, tj, px), fmaf(dy, tj, py), fmaf(dz, tj, pz),
                                                      __fadd_rn((float)(k - 1), tj), sh, sdn);
                     ncoll += sh ? 1 : 0;
                     if (has_dist) a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, sdn)));
@@ -381,7 +430,7 @@ __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_para
         const float prox = warp_sum_xor(a_prox);
         if (lane == c) out.prox = prox;
     }
-    if constexpr (EXTRA) {
+    if constexpr (XF >= 1) {
         if (e.hazard != nullptr) {
             const float haz = warp_sum_xor(a_haz);
             if (lane == c) out.haz = haz;
@@ -390,14 +439,14 @@ __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_para
 }
 
 // Phase C: the score arithmetic of HR:45-59 for this lane's chromosome.
-template <int NW, bool EXTRA>
+template <int NW, int XF>
 __device__ __forceinline__ float combine_fitness(const EnvDev& e, const tf_params& prm, const TileSums<NW>& s) {
     const float tf_ = (float)(s.packed & 1023);
     const float pen = __fadd_rn((float)(s.packed >> 10), s.prox);            // HR:45-46
     const float safety = __fdiv_rn(1.0f, __fadd_rn(1.0f, pen));              // HR:47
     const float energy = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(1.0f, tf_), s.alt));  // HR:48
     float windden = __fadd_rn(1.0f, s.alt);                                  // HR:49
-    if constexpr (EXTRA) {
+    if constexpr (XF >= 1) {
         if (e.hazard != nullptr) windden = fmaf(prm.hazard_weight, s.haz, windden);
     }
     const float wind = __fdiv_rn(1.0f, windden);

@@ -74,7 +74,7 @@ static int run_ga_step(const S* pop, const int32_t* lens, const F* fit, const in
 // Tile structure: phase A (lane = slot) plans 32 children; phase B (lane = waypoint) builds,
 // stores and reduces one child at a time with the next child's parents already in flight;
 // phase C (lane = slot) scores the 32 children and writes fitness / flags coalesced.
-template <int NW, int SEM, bool VOX, bool EXTRA>
+template <int NW, int SEM, bool VOX, int XF>
 __global__ void __launch_bounds__(kBlockThreads)
 generation_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
                   const __grid_constant__ tf_ga_params ga, const float4* __restrict__ pop,
@@ -89,14 +89,14 @@ generation_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_p
     const int nwords = (W + 31) >> 5;
     const int ne = min(ga.n_elite, P);
     const bool uniform = ga.crossover == TF_CX_UNIFORM && tape == nullptr;
-    if ((SEM != TF_SEM_NONE && e.n > 0) || (EXTRA && e.n_dyn > 0)) {
+    if ((SEM != TF_SEM_NONE && e.n > 0) || (XF >= 1 && e.n_dyn_smem > 0)) {
         if (threadIdx.x == 0) {
             mbar_init(sm.bar, 1);
             fence_mbar_init();
         }
         __syncthreads();
         if (threadIdx.x == 0)
-            stage_chunk(e, sm.A, sm.B, 0, min(e.n, kTableCap), sm.bar, EXTRA && e.n_dyn > 0, sm.dA, sm.dB);
+            stage_chunk(e, sm.A, sm.B, 0, min(e.n, kTableCap), sm.bar, XF >= 1 && e.n_dyn_smem > 0, sm.dA, sm.dB);
         mbar_wait(sm.bar, 0);
     }
     const int ntiles = (P + T - 1) / T;
@@ -143,7 +143,7 @@ generation_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_p
             PointAcc<NW, SEM> acc;
             acc.reset();
             if constexpr (SEM != TF_SEM_NONE) eval_static_chunk<SEM, NW>(e, tabs, 0, e.n, cur.x, cur.y, cur.z, acc.hit, acc.best);
-            reduce_chromosome<NW, SEM, VOX, EXTRA>(e, prm, tabs, cur, W, acc, c, sums);
+            reduce_chromosome<NW, SEM, VOX, XF>(e, prm, tabs, cur, W, acc, c, sums);
             cur = nxt;
 #pragma unroll
             for (int s = 0; s < NW; ++s) cw4[s] = nw4[s];
@@ -151,7 +151,7 @@ generation_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_p
         // phase C
         if (lane < cnt) {
             const int slot = slot0 + lane;
-            next_fit[slot] = combine_fitness<NW, EXTRA>(e, prm, sums);
+            next_fit[slot] = combine_fitness<NW, XF>(e, prm, sums);
             if (next_coll) {
 #pragma unroll
                 for (int s = 0; s < NW; ++s)
@@ -167,9 +167,9 @@ struct GenArgs {
     float* next; float* next_fit; uint32_t* next_coll; int32_t* sel; int32_t* cpo; cudaStream_t st;
 };
 
-template <int NW, int SEM, bool VOX, bool EXTRA>
+template <int NW, int SEM, bool VOX, int XF>
 static int launch_generation(const GenArgs& a) {
-    auto kern = generation_kernel<NW, SEM, VOX, EXTRA>;
+    auto kern = generation_kernel<NW, SEM, VOX, XF>;
     size_t smem = smem_bytes_for(*a.e);
     if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int T = tile_size_for(a.P);
@@ -184,11 +184,15 @@ static int launch_generation(const GenArgs& a) {
 template <int NW, int SEM>
 static int gen_flags(const GenArgs& a) {
     const bool vox = a.e->bricks != nullptr;
-    const bool extra = a.e->n_dyn > 0 || a.e->hazard != nullptr || a.prm->samples_per_segment > 1;
-    if (vox && extra) return launch_generation<NW, SEM, true, true>(a);
-    if (vox) return launch_generation<NW, SEM, true, false>(a);
-    if (extra) return launch_generation<NW, SEM, false, true>(a);
-    return launch_generation<NW, SEM, false, false>(a);
+    const int xf = a.prm->samples_per_segment > 1 ? 2 : ((a.e->n_dyn > 0 || a.e->hazard != nullptr) ? 1 : 0);
+    if (vox) {
+        if (xf == 2) return launch_generation<NW, SEM, true, 2>(a);
+        if (xf == 1) return launch_generation<NW, SEM, true, 1>(a);
+        return launch_generation<NW, SEM, true, 0>(a);
+    }
+    if (xf == 2) return launch_generation<NW, SEM, false, 2>(a);
+    if (xf == 1) return launch_generation<NW, SEM, false, 1>(a);
+    return launch_generation<NW, SEM, false, 0>(a);
 }
 template <int NW>
 static int gen_sem(const GenArgs& a) {

@@ -51,13 +51,13 @@ constexpr int kRankThreads = 256;
 
 // values != nullptr : level 0, build keys from fitness values; else keys_in holds survivors.
 template <typename Key, typename T>
-__global__ void __launch_bounds__(kRankThreads)
+__global__ void __launch_bounds__(1024)
 topk_tile_kernel(const T* __restrict__ values, const Key* __restrict__ keys_in, int n, int tile, int k, int worst,
                  Key* __restrict__ keys_out, int32_t* __restrict__ idx_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Key* s = reinterpret_cast<Key*>(smem_raw);
     const int base = blockIdx.x * tile;
-    for (int i = threadIdx.x; i < tile; i += kRankThreads) {
+    for (int i = threadIdx.x; i < tile; i += blockDim.x) {
         const int g = base + i;
         Key key = Key::pad();
         if (g < n) key = values ? Key::make(values[g], (uint32_t)g, worst != 0) : keys_in[g];
@@ -66,7 +66,7 @@ topk_tile_kernel(const T* __restrict__ values, const Key* __restrict__ keys_in, 
     __syncthreads();
     for (int k2 = 2; k2 <= tile; k2 <<= 1) {
         for (int j = k2 >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < (tile >> 1); i += kRankThreads) {
+            for (int i = threadIdx.x; i < (tile >> 1); i += blockDim.x) {
                 const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
                 const int hi = lo | j;
                 const bool up = (lo & k2) == 0;
@@ -78,9 +78,9 @@ topk_tile_kernel(const T* __restrict__ values, const Key* __restrict__ keys_in, 
     }
     const int kk = min(k, tile);
     if (idx_out) {
-        for (int i = threadIdx.x; i < k; i += kRankThreads) idx_out[i] = i < kk ? (int32_t)s[i].index(worst != 0) : -1;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) idx_out[i] = i < kk ? (int32_t)s[i].index(worst != 0) : -1;
     } else {
-        for (int i = threadIdx.x; i < kk; i += kRankThreads) keys_out[(size_t)blockIdx.x * k + i] = s[i];
+        for (int i = threadIdx.x; i < kk; i += blockDim.x) keys_out[(size_t)blockIdx.x * k + i] = s[i];
     }
 }
 
@@ -275,7 +275,7 @@ static int run_select(const float* values, int P, int k, int worst, int32_t* idx
     const size_t smem = (size_t)tile * sizeof(Key32);
     auto kern = topk_tile_kernel<Key32, float>;
     if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<1, kRankThreads, smem, st>>>(nullptr, keys, k, tile, k, worst, nullptr, idx);
+    kern<<<1, tile >= 4096 ? 1024 : kRankThreads, smem, st>>>(nullptr, keys, k, tile, k, worst, nullptr, idx);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

@@ -26,7 +26,7 @@ __host__ __device__ inline size_t stream_smem_bytes(const EnvDev& e, int W) {
 }
 
 // Score bookkeeping of one full-length chromosome whose waypoints sit in shared memory.
-template <int NW, int SEM, bool VOX, bool EXTRA>
+template <int NW, int SEM, bool VOX, int XF>
 __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& prm, const Tables& t,
                                              const Lanes<NW>& cur, const Lanes<NW>& prev, const uint32_t (&vword)[NW],
                                              const uint32_t (&vmask)[NW], PointAcc<NW, SEM>& acc, int c,
@@ -36,11 +36,11 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
     float a_prox = 0.0f, a_dist = 0.0f, a_alt = 0.0f, a_haz = 0.0f;
     int turns = 0, ncoll = 0;
     uint32_t hit = acc.hit;
-    const bool has_dist = (SEM != TF_SEM_NONE) || (EXTRA && e.n_dyn > 0);
+    const bool has_dist = (SEM != TF_SEM_NONE) || (XF >= 1 && e.n_dyn > 0);
     float dn[NW];
 #pragma unroll
     for (int s = 0; s < NW; ++s) dn[s] = (SEM == TF_SEM_HR) ? __fsqrt_rn(acc.best[s]) : acc.best[s];
-    if constexpr (EXTRA) {
+    if constexpr (XF >= 1) {
         if (e.n_dyn > 0) {
             float m2[NW], tm[NW];
 #pragma unroll
@@ -53,7 +53,7 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
             for (int s = 0; s < NW; ++s) dn[s] = fminf(dn[s], __fsqrt_rn(m2[s]));
         }
     }
-    const int S = EXTRA ? max(prm.samples_per_segment, 1) : 1;
+    const int S = (XF >= 2) ? max(prm.samples_per_segment, 1) : 1;
 #pragma unroll
     for (int s = 0; s < NW; ++s) {
         const int k = lane + 32 * s;
@@ -63,7 +63,7 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
         if (lane == c) out.cw[s] = word;
         ncoll += h ? 1 : 0;
         if (has_dist) a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[s])));  // HR:46
-        if constexpr (EXTRA) {
+        if constexpr (XF >= 1) {
             if (e.hazard != nullptr) a_haz = __fadd_rn(a_haz, hazard_sample(e, cur.x[s], cur.y[s], (float)k));
         }
         if (s > 0 || lane > 0) {  // k >= 1
@@ -72,12 +72,12 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
             a_dist = __fadd_rn(a_dist, __fsqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
             a_alt = __fadd_rn(a_alt, fabsf(dz));                         // HR:44
             if (k <= W - 2) turns += (cur.x[s] != px || cur.y[s] != py) ? 1 : 0;  // HR:38-40,43
-            if constexpr (EXTRA) {
+            if constexpr (XF >= 2) {
                 for (int j = 1; j < S; ++j) {  // extension: samples inside segment (k-1, k)
                     float tj = __fdiv_rn((float)j, (float)S);
                     bool sh;
                     float sdn;
-                    eval_point_full<SEM, VOX, EXTRA>(e, t, fmaf(dx, tj, px), fmaf(dy, tj, py), fmaf(dz, tj, pz),
+                    eval_point_full<SEM, VOX, XF>(e, t, fmaf(dx, tj, px), fmaf(dy, tj, py), fmaf(dz, tj, pz),
                                                      __fadd_rn((float)(k - 1), tj), sh, sdn);
                     ncoll += sh ? 1 : 0;
                     if (has_dist) a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, sdn)));
@@ -92,7 +92,7 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
         const float prox = warp_sum_xor(a_prox);
         if (lane == c) out.prox = prox;
     }
-    if constexpr (EXTRA) {
+    if constexpr (XF >= 1) {
         if (e.hazard != nullptr) {
             const float haz = warp_sum_xor(a_haz);
             if (lane == c) out.haz = haz;
@@ -102,8 +102,8 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
 
 // GA = true : fused generation (plan, gather both parents, mutate, store child, evaluate)
 // GA = false: fitness sweep (row p, no store)
-template <int NW, int SEM, bool VOX, bool EXTRA, bool GA>
-__global__ void __launch_bounds__(kBlockThreads)
+template <int NW, int SEM, bool VOX, int XF, bool GA>
+__global__ void __launch_bounds__(kBlockThreads, XF == 1 ? 3 : 1)  // XF 1: latency-bound gathers want >= 24 warps / SM
 stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
               const __grid_constant__ tf_ga_params ga, const float4* __restrict__ pop,
               const float* __restrict__ fit, const int32_t* __restrict__ top_idx,
@@ -125,12 +125,12 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 #pragma unroll
         for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);
     }
-    if ((SEM != TF_SEM_NONE && e.n > 0) || (EXTRA && e.n_dyn > 0)) {
+    if ((SEM != TF_SEM_NONE && e.n > 0) || (XF >= 1 && e.n_dyn_smem > 0)) {
         if (threadIdx.x == 0) mbar_init(sm.bar, 1);
         fence_mbar_init();
         __syncthreads();
         if (threadIdx.x == 0)
-            stage_chunk(e, sm.A, sm.B, 0, min(e.n, kTableCap), sm.bar, EXTRA && e.n_dyn > 0, sm.dA, sm.dB);
+            stage_chunk(e, sm.A, sm.B, 0, min(e.n, kTableCap), sm.bar, XF >= 1 && e.n_dyn_smem > 0, sm.dA, sm.dB);
         mbar_wait(sm.bar, 0);
     } else {
         fence_mbar_init();
@@ -241,7 +241,7 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
             PointAcc<NW, SEM> acc;
             acc.reset();
             if constexpr (SEM != TF_SEM_NONE) eval_static_chunk<SEM, NW>(e, tabs, 0, e.n, cur.x, cur.y, cur.z, acc.hit, acc.best);
-            reduce_fullw<NW, SEM, VOX, EXTRA>(e, prm, tabs, cur, prev, v0w, v0m, acc, c, sums);
+            reduce_fullw<NW, SEM, VOX, XF>(e, prm, tabs, cur, prev, v0w, v0m, acc, c, sums);
             __syncwarp();  // every lane is done with this ring slot: refill it
             if (c + kStages < cnt) issue(c + kStages, head);
             head = st_next;
@@ -251,7 +251,7 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
         // ---- phase C (lane = slot)
         if (lane < cnt) {
             const int slot = slot0 + lane;
-            out_fit[slot] = combine_fitness<NW, EXTRA>(e, prm, sums);
+            out_fit[slot] = combine_fitness<NW, XF>(e, prm, sums);
             if (out_coll) {
 #pragma unroll
                 for (int s = 0; s < NW; ++s) out_coll[(size_t)slot * NW + s] = sums.cw[s];
@@ -266,9 +266,9 @@ struct StreamArgs {
     float* next; float* out_fit; uint32_t* out_coll; int32_t* sel; int32_t* cpo; cudaStream_t st;
 };
 
-template <int NW, int SEM, bool VOX, bool EXTRA, bool GA>
+template <int NW, int SEM, bool VOX, int XF, bool GA>
 static int launch_stream(const StreamArgs& a) {
-    auto kern = stream_kernel<NW, SEM, VOX, EXTRA, GA>;
+    auto kern = stream_kernel<NW, SEM, VOX, XF, GA>;
     const size_t smem = stream_smem_bytes(*a.e, a.W);
     if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int T = tile_size_for(a.P);
@@ -283,11 +283,15 @@ static int launch_stream(const StreamArgs& a) {
 template <int NW, int SEM, bool GA>
 static int stream_flags(const StreamArgs& a) {
     const bool vox = a.e->bricks != nullptr;
-    const bool extra = a.e->n_dyn > 0 || a.e->hazard != nullptr || a.prm->samples_per_segment > 1;
-    if (vox && extra) return launch_stream<NW, SEM, true, true, GA>(a);
-    if (vox) return launch_stream<NW, SEM, true, false, GA>(a);
-    if (extra) return launch_stream<NW, SEM, false, true, GA>(a);
-    return launch_stream<NW, SEM, false, false, GA>(a);
+    const int xf = a.prm->samples_per_segment > 1 ? 2 : ((a.e->n_dyn > 0 || a.e->hazard != nullptr) ? 1 : 0);
+    if (vox) {
+        if (xf == 2) return launch_stream<NW, SEM, true, 2, GA>(a);
+        if (xf == 1) return launch_stream<NW, SEM, true, 1, GA>(a);
+        return launch_stream<NW, SEM, true, 0, GA>(a);
+    }
+    if (xf == 2) return launch_stream<NW, SEM, false, 2, GA>(a);
+    if (xf == 1) return launch_stream<NW, SEM, false, 1, GA>(a);
+    return launch_stream<NW, SEM, false, 0, GA>(a);
 }
 template <int NW, bool GA>
 static int stream_sem(const StreamArgs& a) {
@@ -299,16 +303,12 @@ static int stream_sem(const StreamArgs& a) {
 }
 template <bool GA>
 static int stream_dispatch(const StreamArgs& a) {
-    switch (a.W / 32) {
-    case 1: return stream_sem<1, GA>(a);
-    case 2: return stream_sem<2, GA>(a);
-    default: return stream_sem<4, GA>(a);
-    }
+    return a.W == 32 ? stream_sem<1, GA>(a) : stream_sem<2, GA>(a);
 }
 
 // Host-side eligibility: full-length chromosomes, single table chunk, contiguous parent pieces.
 inline bool stream_eligible(const EnvDev& e, int W, bool uniform_mask) {
-    if (W % 32 != 0 || W > 128 || W == 96 || uniform_mask || e.n > kTableCap) return false;
+    if ((W != 32 && W != 64) || uniform_mask || e.n > kTableCap) return false;
     return stream_smem_bytes(e, W) <= 200 * 1024;
 }
 
