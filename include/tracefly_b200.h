@@ -249,6 +249,11 @@ int tf_replace_worst(float* pop_dev, float* fit_dev, const int32_t* worst_idx_de
                      const float* gathered_rows_dev, const float* gathered_fit_dev,
                      int world, int self_rank, int E, void* stream);
 
+/* ---- backend GA fitness --------------------------------------------------- */
+/* GeneticAlgorithm.fitness_function of uav-backend/app/routers/GA_enhanced.py (GAE:20-26) for a ragged
+ * population: fit_dev i32[P] = -len - #{i in [1, len-2] : path[i-1] != path[i+1]}. */
+int tf_fitness_gae(const float* pop_dev, const int32_t* lens_dev, int P, int W, int32_t* fit_dev, void* stream);
+
 /* ---- compact host format -------------------------------------------------- */
 /* int16[n][4] (x, y, z, pad) <-> f32[n][4]: lattice chromosomes at 8 B per waypoint for the PCIe leg.
  * Packing rounds to nearest and saturates; it is exact for integer coordinates in [-32768, 32767]. */

@@ -196,6 +196,15 @@ def ga_step(pop, fit, top_idx, ga, tape=None, seed=0, gen=0, lens=None):
     return nxt, nlens, sel, cp
 
 
+def fitness_gae(pop, lens=None):
+    pop = np.ascontiguousarray(pop, np.float32)
+    P, W, _ = pop.shape
+    fit = np.zeros(P, np.int32)
+    lens_c = None if lens is None else np.ascontiguousarray(lens, np.int32)
+    lib().orc_fitness_gae(_p(pop), _p(lens_c), P, W, _p(fit))
+    return fit
+
+
 def voxel_words(nx, ny, nz):
     return (nx // 8) * (ny // 8) * (nz // 8) * 16
 

@@ -339,7 +339,7 @@ def gen_evolve_pf(pf):
 def main():
     hr = ref_loader.load_hr()
     pf = ref_loader.load_pf()
-    which = set(sys.argv[1:]) or {"fitness", "evolve"}
+    which = set(sys.argv[1:]) or {"fitness", "evolve", "gae"}
     if "fitness" in which:
         gen_fitness_hr(hr)
         gen_fitness_pf(pf)
@@ -357,6 +357,42 @@ def main():
         obs_cfg1 = [{"position": [int(v) for v in o["position"]], "size": int(o["size"])} for o in env.obstacles]
         gen_evolve_hr(hr, pf, "cfg1", 100, 0.1, 200, (0, 0, 0), (19, 19, 8), obs_cfg1, seed=0)
         gen_evolve_pf(pf)
+    if "gae" in which:
+        gen_run_gae()
+
+
+
+
+# --------------------------------------------------------------------------- GAE (backend GA) run
+def gen_run_gae():
+    """uav-backend/app/routers/GA_enhanced.py GeneticAlgorithm.run at fixed seeds (GAE:60-66), on its
+    own voxel Environment (GAE:87-122).  `mutate` reads a module-global `environment` (GAE:47); the
+    class definitions are exec'ed with that global bound to the environment under test."""
+    gae = ref_loader.load_gae_classes()
+    random.seed(11)
+    np.random.seed(11)
+    env = gae.Environment((0, 30), (0, 30), (0, 15))
+    gae.GeneticAlgorithm.mutate.__globals__["environment"] = env
+    ga = gae.GeneticAlgorithm(population_size=20, generations=30, mutation_rate=0.2)
+    import contextlib, io
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        best = ga.run((0, 0, 0), (30, 30, 15), env)
+    bests = [int(l.split(":")[-1]) for l in buf.getvalue().strip().splitlines()]
+    final = ga.population
+    P = len(final)
+    Wmax = max(len(p) for p in final)
+    wp = np.zeros((P, Wmax, 3))
+    lens = np.zeros(P, np.int32)
+    for i, p in enumerate(final):
+        lens[i] = len(p)
+        wp[i, :len(p)] = np.array(p, np.float64)
+    fit = np.array([ga.fitness_function(p) for p in final], np.int64)
+    meta = dict(META, ref="GAE:6-66,87-179", seed=11, P=20, G=30, rate=0.2)
+    np.savez_compressed(os.path.join(HERE, "run_gae.npz"), wp=wp, lens=lens, fitness=fit, best=np.array(best, np.float64),
+                        best_per_generation=np.array(bests, np.int64),
+                        obstacles=np.array(sorted(env.obstacles), np.int64), meta=np.array(json.dumps(meta)))
+    print("run_gae.npz: final lens", sorted(set(lens.tolist())), "best fitness", bests[-1])
 
 
 if __name__ == "__main__":

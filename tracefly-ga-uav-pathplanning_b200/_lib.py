@@ -73,6 +73,7 @@ _SIGS = {
     "tf_init_walks": (_i, [_u64, _vp, C.POINTER(_f), C.POINTER(_f), C.POINTER(_f), _i, _i, _vp, _vp]),
     "tf_pack_elites": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "tf_replace_worst": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "tf_fitness_gae": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "tf_unpack_i16": (_i, [_vp, _vp, _i64, _vp]),
     "tf_pack_i16": (_i, [_vp, _vp, _i64, _vp]),
     "tf_version": (_i, []),

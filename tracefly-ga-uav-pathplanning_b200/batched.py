@@ -221,6 +221,18 @@ def fitness_batch_f64(pop64, lens, env, params=None, out=None, want_collisions=T
     return fit, coll
 
 
+def fitness_gae(pop, lens):
+    """Backend GA fitness (GAE:20-26) for a ragged population: -> int32[P] cuda."""
+    _chk_tensor(pop, torch.float32, "pop", 3)
+    P, W, _ = pop.shape
+    if lens is not None:
+        _chk_tensor(lens, torch.int32, "lens", 1)
+    fit = torch.empty(P, dtype=torch.int32, device=pop.device)
+    if P:
+        check(lib.tf_fitness_gae(_ptr(pop), _ptr(lens), P, W, _ptr(fit), _stream()), "tf_fitness_gae")
+    return fit
+
+
 def point_query_f64(points, env):
     """is_collision / distance_to_nearest_obstacle (HR:17-28) or is_obstacle / distance_to_obstacles
     (PF:28-59) for a batch of points, float64 reference arithmetic.  points: array-like [n, 3].

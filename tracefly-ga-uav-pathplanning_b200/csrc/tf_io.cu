@@ -50,3 +50,38 @@ extern "C" int tf_pack_i16(const float* pop_dev, int16_t* out_dev, int64_t n_way
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Backend GA (uav-backend/app/routers/GA_enhanced.py) integer fitness, GAE:20-26:
+//   fitness = -len(path) - #{ i in [1, len-2] : path[i-1] != path[i+1] }      (tuple inequality)
+// One warp per path; lanes stride over i.
+namespace tf {
+__global__ void __launch_bounds__(256)
+fitness_gae_kernel(const float4* __restrict__ pop, const int32_t* __restrict__ lens, int P, int W, int32_t* __restrict__ fit) {
+    const int lane = threadIdx.x & 31;
+    for (int p = blockIdx.x * 8 + (threadIdx.x >> 5); p < P; p += gridDim.x * 8) {
+        const int L = lens ? min(lens[p], W) : W;
+        const float4* row = pop + (size_t)p * W;
+        int n = 0;
+        for (int i = 1 + lane; i <= L - 2; i += 32) {
+            const float4 a = row[i - 1], b = row[i + 1];
+            n += (a.x != b.x || a.y != b.y || a.z != b.z) ? 1 : 0;
+        }
+        n = __reduce_add_sync(0xffffffffu, n);
+        if (lane == 0) fit[p] = -L - n;
+    }
+}
+}  // namespace tf
+
+extern "C" int tf_fitness_gae(const float* pop_dev, const int32_t* lens_dev, int P, int W, int32_t* fit_dev, void* stream) {
+    if (!pop_dev || !fit_dev) return TF_ERR_INVALID;
+    if (P < 0 || W < 1) return TF_ERR_SHAPE;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    if (P == 0) return TF_OK;
+    const int grid = (P + 7) / 8 < sm_count() * 8 ? (P + 7) / 8 : sm_count() * 8;
+    tf::fitness_gae_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(pop_dev), lens_dev, P, W,
+                                                                  fit_dev);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
