@@ -232,8 +232,8 @@ def run_gpu(args):
         island.pop, island.nxt = island.nxt, island.pop
         island.fit, island.nfit = island.nfit, island.fit
         island.gen += 1
-        if world > 1 and island.gen % MIGRATE_EVERY == 0:
-            island.migrate()
+        island.after_generation()   # N > 1: pipelined elite exchange (side stream) every 10 generations
+    island.flush()
     t1.record(stream)
     sync_all()
     launches = L.launch_count() - launches0
@@ -330,7 +330,7 @@ def run_gpu(args):
                    "step": "one GA generation = tf_rank_topk + fused tf_generation (tournament k=4, single-point crossover, "
                            "lattice mutation 0.1, 2 elites, Philox4x32-10)",
                    "population_per_gpu": P, "waypoints": W, "islands": world,
-                   "migration": f"{ELITES} elites NCCL all-gather every {MIGRATE_EVERY} generations" if world > 1 else "none (1 island)",
+                   "migration": f"{ELITES} elites NCCL all-gather every {MIGRATE_EVERY} generations, pipelined with the next generation on a side stream" if world > 1 else "none (1 island)",
                    "l2": "inputs larger than L2: population 2 x %.0f MiB ping-pong, voxel grid %d MiB" % (
                        P * W * 16 / 2 ** 20, (cfg["world"][0] * cfg["world"][1] * cfg["world"][2] // 8) >> 20 if cfg["n_voxel_obs"] else 0)},
         "roofline": {"bound": "hbm", "kernel": "stream_kernel<GA> (tf_generation, TMA-staged)", "achieved": achieved, "peak": peak,

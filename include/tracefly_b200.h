@@ -154,6 +154,12 @@ int tf_rank_topk(const float* fit_dev, int P, int k, int worst, int32_t* idx_dev
 int tf_rank_topk_f64(const double* fit64_dev, int P, int k, int worst, int32_t* idx_dev,
                      void* workspace_dev, int64_t workspace_bytes, void* stream);
 
+/* The k best (worst != 0: k worst) chromosomes under the same stable order, as a SET in ASCENDING
+ * INDEX order — no rank order, no sort: the victims of island migration.  Any k <= P. */
+int64_t tf_select_set_workspace_bytes(int P);
+int tf_select_set(const float* fit_dev, int P, int k, int worst, int32_t* idx_dev,
+                  void* workspace_dev, int64_t workspace_bytes, void* stream);
+
 /* ---- selection + crossover + mutation (HR:85-99,114-122; PF:192-208) --------------- */
 
 typedef enum tf_selection {
@@ -244,7 +250,8 @@ int tf_init_walks(uint64_t seed, const float* start_dev /* f32[P][4] or NULL */,
 int tf_pack_elites(const float* pop_dev, const float* fit_dev, const int32_t* elite_idx_dev, int E, int W,
                    float* rows_dev, float* rfit_dev, void* stream);
 /* gathered rows f32[world][E][W][4] / fit f32[world][E]; the j-th FOREIGN elite (source rank
- * ascending, skipping self_rank, then elite rank) overwrites pop[worst_idx[j]], fit[...]. */
+ * ascending, skipping self_rank, then elite rank) overwrites pop[worst_idx[j]], fit[...].
+ * worst_idx: the (world-1)*E victims, e.g. from tf_select_set(..., worst = 1). */
 int tf_replace_worst(float* pop_dev, float* fit_dev, const int32_t* worst_idx_dev, int W,
                      const float* gathered_rows_dev, const float* gathered_fit_dev,
                      int world, int self_rank, int E, void* stream);

@@ -168,6 +168,11 @@ def topk(fit, k, worst=False):
     return idx
 
 
+def select_set(fit, k, worst=False):
+    """The k best / worst under the stable order, as a set in ascending index order."""
+    return np.sort(topk(fit, k, worst=worst)).astype(np.int32)
+
+
 def philox(key0, key1, c0, c1, c2, c3):
     out = (C.c_uint32 * 4)()
     lib().orc_philox4x32_10(C.c_uint32(key0), C.c_uint32(key1), C.c_uint32(c0), C.c_uint32(c1), C.c_uint32(c2),

@@ -261,3 +261,15 @@ def test_host_stepper_round_trip(tf, fmt):
         assert torch.equal(nxt.to(hdt).cpu(), next_h)
     h2d, d2h = stepper.bytes_per_step()
     assert h2d == P * W * 4 * (4 if fmt == "f32" else 2)
+
+
+@pytest.mark.parametrize("P,k", [(1, 1), (5000, 37), (300_000, 1024), (1_000_003, 7168), (70_000, 69_999)])
+def test_select_set_is_the_topk_set_in_index_order(tf, P, k):
+    torch, L, B = tf
+    rng = np.random.default_rng(P + k)
+    vals = (rng.integers(0, max(2, P // 40), size=P).astype(np.float32) / 3.0)
+    fit = torch.from_numpy(vals).cuda()
+    sel = B.SelectSet(P, k)
+    for worst in (False, True):
+        got = sel(fit, worst=worst).cpu().numpy()
+        assert np.array_equal(got, O.select_set(vals, k, worst=worst))

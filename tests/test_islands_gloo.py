@@ -38,11 +38,13 @@ class OracleOps:
         out_pop.copy_(torch.from_numpy(nxt))
         out_fit.copy_(torch.from_numpy(self.O.fitness_f32(self.oenv, nxt)[0]))
 
-    def elites(self, fit):
-        return torch.from_numpy(self.O.topk(fit.numpy(), self.E))
+    def elites(self, fit, out):
+        out.copy_(torch.from_numpy(self.O.topk(fit.numpy(), self.E)))
+        return out
 
-    def worst(self, fit):
-        return torch.from_numpy(self.O.topk(fit.numpy(), self.n_worst, worst=True))
+    def worst(self, fit, out):
+        out.copy_(torch.from_numpy(self.O.select_set(fit.numpy(), self.n_worst, worst=True)))
+        return out
 
     def pack(self, pop, fit, idx, rows, rfit):
         r, f = self.O.pack_elites(pop.numpy(), fit.numpy(), idx.numpy())
@@ -63,7 +65,7 @@ def _world(rank):
     return O, oenv, pop
 
 
-def _worker(rank, world, port, outdir):
+def _worker(rank, world, port, outdir, pipelined):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from tracefly_b200 import _lib as L
@@ -71,43 +73,59 @@ def _worker(rank, world, port, outdir):
     O, oenv, pop = _world(rank)
     ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=3, mutation_rate=0.3)
     ops = OracleOps(oenv, 2, E, (world - 1) * E)
-    isl = IslandGA(torch.from_numpy(pop), ga, seed=SEED, elites=E, interval=INTERVAL, ops=ops)
+    isl = IslandGA(torch.from_numpy(pop), ga, seed=SEED, elites=E, interval=INTERVAL, ops=ops, pipelined=pipelined)
     assert isl.E == E and isl.world == world and isl.ga.stream_id == rank
     for _ in range(GENS):
         isl.step()
+    isl.flush()
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), pop=isl.pop.numpy(), fit=isl.fit.numpy(), mig=isl.migrations)
     dist.destroy_process_group()
 
 
-def _simulate(world):
-    """Single-process restatement of the same island schedule."""
+def _simulate(world, pipelined):
+    """Single-process restatement of the island schedule.  Pipelined: the elites of generation g
+    (g % INTERVAL == 0) replace the worst of generation g+1 (victims in ascending index order)."""
     from oracle import c_oracle as O
     st = []
     for r in range(world):
         _, oenv, pop = _world(r)
         st.append(dict(env=oenv, pop=pop, fit=O.fitness_f32(oenv, pop)[0]))
+    pending = None
+
+    def insert(packs):
+        grows = np.stack([p[0] for p in packs])
+        gfit = np.stack([p[1] for p in packs])
+        for r, s in enumerate(st):
+            worst = O.select_set(s["fit"], (world - 1) * E, worst=True)
+            O.replace_worst(s["pop"], s["fit"], worst, grows, gfit, world, r, E)
+
     for gen in range(GENS):
         for r, s in enumerate(st):
             ga = O.default_ga(selection=1, tournament_k=3, mutation_rate=0.3, stream_id=r)
             s["pop"], _, _, _ = O.ga_step(s["pop"], s["fit"], O.topk(s["fit"], 2), ga, seed=SEED, gen=gen)
             s["fit"] = O.fitness_f32(s["env"], s["pop"])[0]
+        if pending is not None:
+            insert(pending)
+            pending = None
         if (gen + 1) % INTERVAL == 0:
             packs = [O.pack_elites(s["pop"], s["fit"], O.topk(s["fit"], E)) for s in st]
-            worst = [O.topk(s["fit"], (world - 1) * E, worst=True) for s in st]
-            grows = np.stack([p[0] for p in packs])
-            gfit = np.stack([p[1] for p in packs])
-            for r, s in enumerate(st):
-                O.replace_worst(s["pop"], s["fit"], worst[r], grows, gfit, world, r, E)
+            if pipelined:
+                pending = packs
+            else:
+                insert(packs)
+    if pending is not None:
+        insert(pending)
     return st
 
 
-def test_two_islands_over_gloo(tmp_path):
+@pytest.mark.parametrize("pipelined", [True, False])
+def test_two_islands_over_gloo(tmp_path, pipelined):
     import __graft_entry__ as g
     g.build()
     world = 2
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
-    ref = _simulate(world)
+    port = 29500 + (os.getpid() % 2000) + (7 if pipelined else 0)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), pipelined), nprocs=world, join=True)
+    ref = _simulate(world, pipelined)
     for r in range(world):
         got = np.load(tmp_path / f"rank{r}.npz")
         assert int(got["mig"]) == GENS // INTERVAL

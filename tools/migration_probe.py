@@ -24,16 +24,13 @@ for rep in range(5):
     def mark(name):
         e = ev(); e.record(); marks.append((name, e, time.perf_counter()))
     mark("start")
-    el = isl.ops.elites(isl.fit); mark("topk_elites")
     E, W = isl.E, isl.W
-    rows = isl.send[:E * W * 4].view(E, W, 4); rfit = isl.send[E * W * 4:]
-    isl.ops.pack(isl.pop, isl.fit, el, rows, rfit); mark("pack")
-    worst = isl.ops.worst(isl.fit); mark("topk_worst")
     if world > 1:
-        dist.all_gather_into_tensor(isl.recv, isl.send); mark("all_gather")
-        g = isl.recv.view(world, isl.send.numel())
-        grows = g[:, :E * W * 4].contiguous(); gfit = g[:, E * W * 4:].contiguous(); mark("contiguous")
-        isl.ops.replace(isl.pop, isl.fit, worst, grows, gfit, world, rank, E); mark("replace")
+        isl.ops.elites(isl.fit, isl.elite_idx); mark("topk_elites")
+        isl.ops.pack(isl.pop, isl.fit, isl.elite_idx, isl.send_rows, isl.send_fit); mark("pack")
+        dist.all_gather_into_tensor(isl.recv_rows, isl.send_rows); dist.all_gather_into_tensor(isl.recv_fit, isl.send_fit); mark("all_gather")
+        isl.ops.worst(isl.fit, isl.worst_idx); mark("select_worst_set")
+        isl.ops.replace(isl.pop, isl.fit, isl.worst_idx, isl.recv_rows, isl.recv_fit, world, rank, E); mark("replace")
     torch.cuda.synchronize()
     for (n0, e0, t0), (n1, e1, t1) in zip(marks[:-1], marks[1:]):
         res.setdefault(n1, []).append((e0.elapsed_time(e1) * 1e3, (t1 - t0) * 1e6))

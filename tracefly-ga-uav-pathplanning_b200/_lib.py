@@ -62,6 +62,8 @@ _SIGS = {
     "tf_topk_workspace_bytes": (_i64, [_i, _i, _i]),
     "tf_rank_topk": (_i, [_vp, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "tf_rank_topk_f64": (_i, [_vp, _i, _i, _i, _vp, _vp, _i64, _vp]),
+    "tf_select_set_workspace_bytes": (_i64, [_i]),
+    "tf_select_set": (_i, [_vp, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "tf_ga_step": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(GaParams), _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "tf_ga_step_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(GaParams), _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "tf_generation": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(GaParams), C.POINTER(Params), _i, _i,

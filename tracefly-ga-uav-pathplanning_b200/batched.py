@@ -270,6 +270,25 @@ class TopK:
         return idx
 
 
+class SelectSet:
+    """The k best / worst chromosomes as a set in ascending index order (tf_select_set)."""
+
+    def __init__(self, P, k, device="cuda"):
+        self.P, self.k = P, k
+        nbytes = lib.tf_select_set_workspace_bytes(P)
+        if nbytes < 0 or k < 1 or k > P:
+            raise ValueError(f"select_set: unsupported P={P}, k={k}")
+        self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        self.nbytes = int(nbytes)
+
+    def __call__(self, fit, worst=False, out=None):
+        _chk_tensor(fit, torch.float32, "fit", 1)
+        idx = out if out is not None else torch.empty(self.k, dtype=torch.int32, device=fit.device)
+        check(lib.tf_select_set(_ptr(fit), self.P, self.k, int(worst), _ptr(idx), _ptr(self.ws), self.nbytes, _stream()),
+              "tf_select_set")
+        return idx
+
+
 def rank_topk(fit, k, worst=False):
     return TopK(fit.numel(), k, f64=fit.dtype == torch.float64, device=fit.device)(fit, worst)
 

@@ -281,6 +281,114 @@ static int run_select(const float* values, int P, int k, int worst, int32_t* idx
 }
 static int run_select(const double*, int, int, int, int32_t*, void*, int64_t, cudaStream_t) { return TF_ERR_UNSUPPORTED; }
 
+// ------------------------------------------------------------------------------------------
+// The k best (or worst) chromosomes as a SET, returned in ascending index order: the same radix
+// select pins the k-th key, then an ordered compaction (per-block counts -> scan -> scatter)
+// replaces the final sort.  Used for the victims of island migration, where only a deterministic
+// assignment matters, not the rank order (k = (world-1) * E = 7168 at 8 GPUs).
+constexpr int kSetBlock = 1024;  // elements per block of the ordered compaction (256 threads x 4)
+
+__global__ void __launch_bounds__(256)
+set_count_kernel(const float* __restrict__ values, int P, int worst, const SelState* __restrict__ st,
+                 unsigned int* __restrict__ block_counts) {
+    __shared__ unsigned int total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    const unsigned long long K = st->prefix;
+    unsigned int n = 0;
+    for (int j = 0; j < 4; ++j) {
+        const int i = blockIdx.x * kSetBlock + j * 256 + threadIdx.x;
+        if (i < P) n += Key32::make(values[i], (uint32_t)i, worst != 0).v <= K ? 1u : 0u;
+    }
+    n = __reduce_add_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&total, n);
+    __syncthreads();
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) set_scan_kernel(unsigned int* __restrict__ block_counts, int nblocks) {
+    __shared__ unsigned int part[1024];
+    const int per = (nblocks + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(nblocks, lo + per);
+    unsigned int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += block_counts[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        unsigned int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned int run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
+    for (int i = lo; i < hi; ++i) {  // exclusive offsets, in place
+        const unsigned int c = block_counts[i];
+        block_counts[i] = run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+set_scatter_kernel(const float* __restrict__ values, int P, int worst, int k, const SelState* __restrict__ st,
+                   const unsigned int* __restrict__ block_offsets, int32_t* __restrict__ idx) {
+    __shared__ unsigned int warp_tot[4][8];
+    const unsigned long long K = st->prefix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool sel[4];
+    unsigned int mask[4];
+    for (int j = 0; j < 4; ++j) {
+        const int i = blockIdx.x * kSetBlock + j * 256 + threadIdx.x;
+        sel[j] = i < P && Key32::make(values[i], (uint32_t)i, worst != 0).v <= K;
+        mask[j] = __ballot_sync(0xffffffffu, sel[j]);
+        if (lane == 0) warp_tot[j][warp] = __popc(mask[j]);
+    }
+    __syncthreads();
+    unsigned int base = block_offsets[blockIdx.x];
+    for (int j = 0; j < 4; ++j) {  // element order inside the block: j-major, then thread
+        unsigned int before = 0;
+        for (int w = 0; w < warp; ++w) before += warp_tot[j][w];
+        if (sel[j]) {
+            const unsigned int pos = base + before + __popc(mask[j] & ((1u << lane) - 1u));
+            if (pos < (unsigned int)k) idx[pos] = blockIdx.x * kSetBlock + j * 256 + threadIdx.x;
+        }
+        for (int w = 0; w < 8; ++w) base += warp_tot[j][w];
+    }
+}
+
+static int64_t set_workspace_bytes(int P) {
+    return 256 + 256 + (int64_t)kSelPasses * kSelBins * 4 + (int64_t)((P + kSetBlock - 1) / kSetBlock) * 4 + 256;
+}
+
+static int run_select_set(const float* values, int P, int k, int worst, int32_t* idx, void* ws, int64_t ws_bytes,
+                          cudaStream_t st) {
+    if (!values || !idx) return TF_ERR_INVALID;
+    if (P < 1 || k < 1 || k > P) return TF_ERR_SHAPE;
+    if (!ws || ws_bytes < set_workspace_bytes(P)) return TF_ERR_WORKSPACE;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    char* base = reinterpret_cast<char*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    SelState* state = reinterpret_cast<SelState*>(base);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(base + 256);
+    unsigned int* counts = reinterpret_cast<unsigned int*>(base + 256 + kSelPasses * kSelBins * 4);
+    sel_init_kernel<<<1, 256, 0, st>>>(state, hist, k);
+    TF_LAUNCH_CHECK();
+    const int grid = min((P + 255) / 256, sm_count() * 8);
+    for (int pass = 0; pass < kSelPasses; ++pass) {
+        sel_hist_kernel<<<grid, 256, 0, st>>>(values, P, worst, pass, state, hist);
+        TF_LAUNCH_CHECK();
+        sel_scan_kernel<<<1, 256, 0, st>>>(pass, state, hist);
+        TF_LAUNCH_CHECK();
+    }
+    const int nblocks = (P + kSetBlock - 1) / kSetBlock;
+    set_count_kernel<<<nblocks, 256, 0, st>>>(values, P, worst, state, counts);
+    TF_LAUNCH_CHECK();
+    set_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks);
+    TF_LAUNCH_CHECK();
+    set_scatter_kernel<<<nblocks, 256, 0, st>>>(values, P, worst, k, state, counts, idx);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+
 template <typename Key, typename T>
 static int run_topk(const T* values, int P, int k, int worst, int32_t* idx, void* ws, int64_t ws_bytes, cudaStream_t st) {
     if (!values || !idx) return TF_ERR_INVALID;
@@ -363,4 +471,10 @@ extern "C" int tf_rank_topk(const float* fit_dev, int P, int k, int worst, int32
 extern "C" int tf_rank_topk_f64(const double* fit64_dev, int P, int k, int worst, int32_t* idx_dev,
                                 void* workspace_dev, int64_t workspace_bytes, void* stream) {
     return run_topk<Key64, double>(fit64_dev, P, k, worst, idx_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int64_t tf_select_set_workspace_bytes(int P) { return P < 1 ? TF_ERR_SHAPE : set_workspace_bytes(P); }
+extern "C" int tf_select_set(const float* fit_dev, int P, int k, int worst, int32_t* idx_dev, void* workspace_dev,
+                             int64_t workspace_bytes, void* stream) {
+    return run_select_set(fit_dev, P, k, worst, idx_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }

@@ -1,17 +1,26 @@
 """Island-model GA (BASELINE configs[4]): the population is split into islands,
 one per GPU / process; islands evolve independently and exchange only their elites — an NCCL
 all-gather over NVLink every `interval` generations.  Each island then overwrites its worst
-(world-1)*E chromosomes with the foreign elites (source rank ascending, then elite rank).
+(world-1)*E chromosomes with the foreign elites (source rank ascending, then elite rank; victims
+taken in ascending index order).
+
+Pipelined migration: the elites of generation g are selected, packed and all-gathered on a SIDE
+stream while the main stream already computes generation g+1; they replace the worst of generation
+g+1 as soon as it exists.  Only the victim selection and the replace kernel stay on the critical
+path.  The schedule is deterministic (it does not depend on timing), and a synchronous `migrate()`
+is kept for warm-up / final flush.
 
 The reference is single-population (HR:115 keeps 2 elites), so there is no reference behaviour
 to match here: a 1-island run is exactly `evolve_batch`, and the N-island exchange is checked
 against the CPU restatement (tests/test_islands_gloo.py, world_size 2 on gloo).
 
-The data path never touches the host: pack (tf_pack_elites) -> all_gather_into_tensor ->
-replace (tf_replace_worst) all run on the island's CUDA stream.  `ops` abstracts the four
-device operations so the same scheduling / ordering logic runs on CPU tensors under gloo in
-the tests (with the oracle's ops) — the product always uses `CudaOps`.
+The data path never touches the host: tf_rank_topk -> tf_pack_elites -> all_gather_into_tensor ->
+tf_select_set -> tf_replace_worst.  `ops` abstracts the device operations so the same scheduling
+logic runs on CPU tensors under gloo in the tests (with the oracle's ops) — the product always
+uses `CudaOps`.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 
@@ -22,13 +31,13 @@ class CudaOps:
     """The product path: every operation is a kernel of libtracefly_b200.so."""
 
     def __init__(self, env, params, P, W, k_rank, E, n_worst):
-        import ctypes as C
         from . import batched as B
-        self.B, self.C = B, C
+        self.B = B
         self.env, self.params = env, params
         self.topk_rank = B.TopK(P, k_rank)
         self.topk_elite = B.TopK(P, E) if E else None
-        self.topk_worst = B.TopK(P, n_worst) if n_worst else None
+        self.worst_set = B.SelectSet(P, n_worst) if n_worst else None
+        self.side = torch.cuda.Stream() if n_worst else None
 
     def fitness(self, pop):
         return self.B.fitness_batch(pop, None, self.env, self.params, want_collisions=False)[0]
@@ -40,14 +49,14 @@ class CudaOps:
         self.B.generation(self.env, pop, fit, top, ga, self.params, seed=seed, generation=gen, out_pop=out_pop,
                           out_fit=out_fit)
 
-    def elites(self, fit):
-        return self.topk_elite(fit)
+    def elites(self, fit, out):
+        return self.topk_elite(fit, out=out)
 
-    def worst(self, fit):
-        return self.topk_worst(fit, worst=True)
+    def worst(self, fit, out):
+        return self.worst_set(fit, worst=True, out=out)
 
     def pack(self, pop, fit, idx, rows, rfit):
-        B, C = self.B, self.C
+        B = self.B
         L.check(L.lib.tf_pack_elites(B._ptr(pop), B._ptr(fit), B._ptr(idx), idx.numel(), pop.shape[1], B._ptr(rows),
                                      B._ptr(rfit), B._stream()), "tf_pack_elites")
 
@@ -56,11 +65,20 @@ class CudaOps:
         L.check(L.lib.tf_replace_worst(B._ptr(pop), B._ptr(fit), B._ptr(worst_idx), pop.shape[1], B._ptr(grows),
                                        B._ptr(gfit), world, rank, E, B._stream()), "tf_replace_worst")
 
+    # ---- stream plumbing of the pipelined migration
+    def on_side_stream(self):
+        self.side.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(self.side)
+
+    def join_side_stream(self):
+        torch.cuda.current_stream().wait_stream(self.side)
+
 
 class IslandGA:
     """One island.  `pop` f32[P, W, 4] lives on this rank's device and is consumed (ping-pong)."""
 
-    def __init__(self, pop, ga, seed=0, elites=1024, interval=10, group=None, ops=None, env=None, params=None):
+    def __init__(self, pop, ga, seed=0, elites=1024, interval=10, group=None, ops=None, env=None, params=None,
+                 pipelined=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
@@ -68,6 +86,7 @@ class IslandGA:
         self.P, self.W = P, W
         self.E = min(elites, P // max(1, 2 * max(self.world - 1, 1))) if self.world > 1 else 0
         self.interval = interval
+        self.pipelined = pipelined
         self.ga = ga
         self.ga.stream_id = self.rank          # Philox streams are keyed by island
         self.seed = seed
@@ -80,46 +99,79 @@ class IslandGA:
         self.pop, self.nxt = pop, torch.empty_like(pop)
         self.fit = ops.fitness(pop)
         self.nfit = torch.empty_like(self.fit)
-        self.top = torch.empty(self.k_rank, dtype=torch.int32, device=pop.device)
+        dev = pop.device
+        self.top = torch.empty(self.k_rank, dtype=torch.int32, device=dev)
         self.gen = 0
         self.migrations = 0
-        if self.world > 1:
-            # one send / receive buffer: E rows of W*4 floats followed by E fitness values
-            self.send = torch.empty(self.E * (W * 4 + 1), dtype=torch.float32, device=pop.device)
-            self.recv = torch.empty(self.world * self.send.numel(), dtype=torch.float32, device=pop.device)
+        self._pending = False
+        if self.world > 1 and self.E > 0:
+            E = self.E
+            self.elite_idx = torch.empty(E, dtype=torch.int32, device=dev)
+            self.worst_idx = torch.empty(n_worst, dtype=torch.int32, device=dev)
+            self.send_rows = torch.empty((E, W, 4), dtype=torch.float32, device=dev)
+            self.send_fit = torch.empty(E, dtype=torch.float32, device=dev)
+            self.recv_rows = torch.empty((self.world, E, W, 4), dtype=torch.float32, device=dev)
+            self.recv_fit = torch.empty((self.world, E), dtype=torch.float32, device=dev)
 
+    # ------------------------------------------------------------------ one generation
     def step(self):
-        """One generation: rank -> select/crossover/mutate + fitness (fused); migrate when due."""
+        """rank -> select/crossover/mutate + fitness (fused); then the migration schedule."""
         self.ops.rank(self.fit, self.top)
         self.ops.generation(self.pop, self.fit, self.top, self.ga, self.seed, self.gen, self.nxt, self.nfit)
         self.pop, self.nxt = self.nxt, self.pop
         self.fit, self.nfit = self.nfit, self.fit
         self.gen += 1
-        if self.world > 1 and self.interval > 0 and self.gen % self.interval == 0:
-            self.migrate()
+        self.after_generation()
 
-    def migrate(self):
-        """pack elites -> all-gather (NCCL over NVLink in production) -> replace worst."""
-        E, W = self.E, self.W
-        if E == 0:
+    def after_generation(self):
+        if self.world <= 1 or self.E == 0 or self.interval <= 0:
             return
-        rows = self.send[:E * W * 4].view(E, W, 4)
-        rfit = self.send[E * W * 4:]
-        self.ops.pack(self.pop, self.fit, self.ops.elites(self.fit), rows, rfit)
-        worst = self.ops.worst(self.fit)            # ranked BEFORE any replacement
-        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
-        per = self.send.numel()
-        g = self.recv.view(self.world, per)
-        if self.recv.is_cuda:
-            # the kernels take [world][E][W][4] rows and [world][E] fitness: views into recv are
-            # strided per rank, so hand them the two sub-blocks rank by rank-contiguous
-            grows = g[:, :E * W * 4].contiguous()
-            gfit = g[:, E * W * 4:].contiguous()
-        else:
-            grows, gfit = g[:, :E * W * 4].contiguous(), g[:, E * W * 4:].contiguous()
-        self.ops.replace(self.pop, self.fit, worst, grows, gfit, self.world, self.rank, E)
+        if self._pending:                       # elites gathered during this generation arrive now
+            self._finish_exchange()
+        if self.gen % self.interval == 0:
+            if self.pipelined:
+                self._start_exchange()
+            else:
+                self.migrate()
+
+    # ------------------------------------------------------------------ migration
+    def _side(self):
+        return self.ops.on_side_stream() if hasattr(self.ops, "on_side_stream") else contextlib.nullcontext()
+
+    def _start_exchange(self):
+        """elites of the CURRENT population -> packed -> all-gathered (side stream on the GPU)."""
+        with self._side():
+            self.ops.elites(self.fit, self.elite_idx)
+            self.ops.pack(self.pop, self.fit, self.elite_idx, self.send_rows, self.send_fit)
+            # output = the inputs of all ranks concatenated along dim 0 (accepted by NCCL and gloo alike)
+            dist.all_gather_into_tensor(self.recv_rows.view(self.world * self.E, self.W, 4), self.send_rows, group=self.group)
+            dist.all_gather_into_tensor(self.recv_fit.view(self.world * self.E), self.send_fit, group=self.group)
+        self._pending = True
+
+    def _finish_exchange(self):
+        """foreign elites overwrite the worst of the CURRENT population."""
+        if hasattr(self.ops, "join_side_stream"):
+            self.ops.join_side_stream()
+        self.ops.worst(self.fit, self.worst_idx)
+        self.ops.replace(self.pop, self.fit, self.worst_idx, self.recv_rows, self.recv_fit, self.world, self.rank, self.E)
+        self._pending = False
         self.migrations += 1
 
+    def migrate(self):
+        """Synchronous exchange on the current population (warm-up, non-pipelined mode)."""
+        if self.world <= 1 or self.E == 0:
+            return
+        if self._pending:
+            self._finish_exchange()
+        self._start_exchange()
+        self._finish_exchange()
+
+    def flush(self):
+        """Apply an exchange that is still in flight (call before reading the final population)."""
+        if self._pending:
+            self._finish_exchange()
+
     def best(self):
+        self.flush()
         f, i = torch.max(self.fit, dim=0)
         return float(f), self.pop[int(i)]
