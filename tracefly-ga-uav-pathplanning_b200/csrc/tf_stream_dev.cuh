@@ -103,7 +103,10 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
 // GA = true : fused generation (plan, gather both parents, mutate, store child, evaluate)
 // GA = false: fitness sweep (row p, no store)
 template <int NW, int SEM, bool VOX, int XF, bool GA>
-__global__ void __launch_bounds__(kBlockThreads, XF == 1 ? 3 : 1)  // XF 1: latency-bound gathers want >= 24 warps / SM
+__global__ void __launch_bounds__(kBlockThreads, (XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? 3 : 0))
+// 32 warps / SM for the HBM-bound plain variant (<= 64 registers), 24 for the gather-heavy XF 1
+// variants (<= 80); the obstacle-loop (FP32-bound) and sampling variants are left to ptxas
+// (measured: forcing 3 or 4 CTAs / SM on the PF variants costs 4-12 %)
 stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
               const __grid_constant__ tf_ga_params ga, const float4* __restrict__ pop,
               const float* __restrict__ fit, const int32_t* __restrict__ top_idx,
