@@ -203,3 +203,21 @@ def test_dynamic_index_equals_brute_force(tf):
                 O.set_threads(1)
             assert np.array_equal(ocoll, as_u32(coll)), (S, cap, band)
             assert np.array_equal(ofit, fit.cpu().numpy()), (S, cap, band)
+
+
+def test_indexed_hr_spheres_equal_plain_hr(tf):
+    """Environment.from_hr_obstacles_indexed (candidate index, zero-velocity spheres) == from_hr_obstacles."""
+    torch, L, B = tf
+    rng = np.random.default_rng(8)
+    world, n, P, W = 256, 1500, 4000, 32
+    obstacles = [{"position": [int(v) for v in rng.integers(0, world, size=3)], "size": int(rng.integers(1, 5))} for _ in range(n)]
+    for o in obstacles[::7]:
+        del o["size"]                       # HR:20 default
+    pop = B.init_walks(3, P, W, lo=(-5, -5, -5), hi=(world + 5,) * 3,
+                       start_per_path=torch.from_numpy(np.concatenate([rng.integers(-3, world + 3, size=(P, 3)), np.zeros((P, 1))], axis=1).astype(np.float32)).cuda())
+    plain = B.Environment.from_hr_obstacles(obstacles, 2.0)
+    fast = B.Environment.from_hr_obstacles_indexed(obstacles, (0, 0, 0), (world,) * 3, cell=16.0, safety_radius=2.0)
+    assert fast.dynamic_index_stats()["overflowed"] == 0
+    f0, c0 = B.fitness_batch(pop, None, plain)
+    f1, c1 = B.fitness_batch(pop, None, fast)
+    assert torch.equal(f0, f1) and torch.equal(c0, c1)

@@ -67,6 +67,23 @@ class Environment:
         return cls(L.SEM_HR, t, safety_radius)
 
     @classmethod
+    def from_hr_obstacles_indexed(cls, obstacles, box_lo, box_hi, cell, safety_radius=2.0, cap=64):
+        """HR rules (HR:17-28) for LARGE sphere sets (up to 2048) through the candidate index: the
+        spheres are stored as moving spheres with zero velocity, so a waypoint only visits the few
+        spheres that can be nearest to / collide with a point of its grid cell.  The arithmetic per
+        sphere is the same (c + 0*t == c), hence results are bit-identical to `from_hr_obstacles`
+        for the FP32 kernels (the float64 reference-order kernels need the plain constructor)."""
+        env = cls(L.SEM_NONE, None, 0.0)
+        env.semantics = L.SEM_HR            # callers pick the HR distance guard from this
+        dyn = np.zeros((len(obstacles), 8), np.float32)
+        for i, o in enumerate(obstacles):
+            dyn[i, 0:3] = np.asarray(o["position"], np.float32)[:3]
+            dyn[i, 3] = float(o["size"]) if "size" in o else -1.0
+        env.set_dynamic(dyn, safety_radius)
+        env.build_dynamic_index(L.W_MAX, box_lo, box_hi, cell, cap=cap, band=L.W_MAX)
+        return env
+
+    @classmethod
     def from_pf_obstacles(cls, obstacles):
         """obstacles: list of {"shape", "position", "size"} (ComplexEnvironment.obstacles, PF:17-26);
         an "aabb" shape with "half": (hx,hy,hz) is accepted as an extension."""
