@@ -146,6 +146,9 @@ def build_gpu_workload(cfg, rank, torch, B, L):
     params = L.default_params(dist_zero_guard=1)
     if cfg["n_analytic"]:
         env = B.Environment(L.SEM_PF, obstacle_table(cfg, cfg["n_analytic"], 4, SEED + 1), 0.0)
+        if os.environ.get("TF_STATIC_INDEX", "1") != "0":   # candidate index: same results, ~20x fewer tests
+            env.build_static_index((0, 0, 0), cfg["world"], cell=float(os.environ.get("TF_STATIC_CELL", 8)), cap=96,
+                                   z_cell=1.0, z_cap=48)
         params.dist_zero_guard = 0
     else:
         env = B.Environment.empty()

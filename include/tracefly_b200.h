@@ -84,6 +84,17 @@ int tf_env_create(int semantics, const tf_obstacle* obs_host, int n, float safet
  * reference-order kernels then see positions / sizes / safety radius unrounded. */
 int tf_env_create_f64(int semantics, const double* obs64_host, int n, double safety_radius, tf_env** out);
 int tf_env_set_dynamic(tf_env* env, const tf_dyn_obstacle* dyn_host, int n, float safety_radius);
+/* Optional acceleration of the static analytic obstacles (HR and PF rules): a uniform grid over
+ * [box_lo, box_hi) whose `cell`-sized cells list (up to `cap`) the spheres / cubes / aabbs that can be
+ * nearest to a point of the cell plus every obstacle that can collide with one, and — PF cylinders
+ * measure distance along z only (PF:56-57) — a 1-D index of `z_cell`-high slabs listing the cylinders
+ * that can be nearest.  A waypoint then visits tens of obstacles instead of all N, and the obstacle
+ * tables are no longer staged in shared memory.  Results are bit-identical to the full loop; points
+ * outside the box and overflowed lists fall back to it. */
+int tf_env_build_static_index(tf_env* env, const float box_lo[3], const float box_hi[3], float cell, int cap,
+                              float z_cell, int z_cap, void* stream);
+int tf_env_static_index_stats(const tf_env* env, int64_t* n_lists, int64_t* n_overflow, double* mean_len,
+                              int* max_len, double* z_mean_len);
 /* Optional acceleration of the moving spheres: a uniform grid over [box_lo, box_hi) with `cell`-sized
  * cells, one copy per band of `band` consecutive integer times, whose entries list (up to `cap`) the
  * spheres that can be nearest to, or collide with, a point of the cell at a time of the band

@@ -221,3 +221,33 @@ def test_indexed_hr_spheres_equal_plain_hr(tf):
     f0, c0 = B.fitness_batch(pop, None, plain)
     f1, c1 = B.fitness_batch(pop, None, fast)
     assert torch.equal(f0, f1) and torch.equal(c0, c1)
+
+
+@pytest.mark.parametrize("sem", ["hr", "pf"])
+@pytest.mark.parametrize("W", [20, 32, 64])
+def test_static_index_equals_full_table_loop(tf, sem, W):
+    """tf_env_build_static_index: bit-identical fitness / flags to the brute-force table loop, for points
+    inside and outside the box, generous and overflowing list capacities, float obstacle data."""
+    torch, L, B = tf
+    rng = np.random.default_rng(W + (7 if sem == "pf" else 0))
+    world, n, P = 128, 900, 3000
+    table = random_table(rng, n, world, sem_pf=(sem == "pf"), aabb=True)
+    table[: n // 3, :3] += rng.uniform(-0.5, 0.5, size=(n // 3, 3))      # non-lattice centres
+    table[: n // 5, 3] = rng.uniform(0.5, 4.0, size=n // 5)              # non-integer sizes
+    semc = L.SEM_PF if sem == "pf" else L.SEM_HR
+    starts = np.concatenate([rng.integers(-6, world + 6, size=(P, 3)), np.zeros((P, 1))], axis=1).astype(np.float32)
+    pop = B.init_walks(5, P, W, lo=(-8, -8, -8), hi=(world + 8,) * 3, start_per_path=torch.from_numpy(starts).cuda())
+    pop[: P // 4, :, :3] += torch.rand((P // 4, W, 3), device="cuda") - 0.5   # non-lattice waypoints too
+    plain = B.Environment(semc, table, 2.0)
+    f0, c0 = B.fitness_batch(pop, None, plain)
+    ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, mutation_rate=0.5)
+    top = B.rank_topk(f0, 2)
+    g0 = B.generation(plain, pop, f0, top, ga, seed=1, generation=0, want_collisions=True)
+    for cell, cap, zc, zcap in ((8.0, 96, 1.0, 32), (16.0, 128, 2.0, 64), (32.0, 6, 4.0, 2)):
+        env = B.Environment(semc, table, 2.0).build_static_index((0, 0, 0), (world,) * 3, cell, cap, zc, zcap)
+        f1, c1 = B.fitness_batch(pop, None, env)
+        assert torch.equal(f0, f1) and torch.equal(c0, c1), (cell, cap)
+        g1 = B.generation(env, pop, f0, top, ga, seed=1, generation=0, want_collisions=True)
+        assert torch.equal(g0[0], g1[0]) and torch.equal(g0[1], g1[1]) and torch.equal(g0[2], g1[2])
+    st = B.Environment(semc, table, 2.0).build_static_index((0, 0, 0), (world,) * 3, 8.0, 96).static_index_stats()
+    assert st["overflowed"] == 0 and st["mean_len"] < 40

@@ -46,6 +46,8 @@ _SIGS = {
     "tf_env_create": (_i, [_i, _vp, _i, _f, C.POINTER(_vp)]),
     "tf_env_create_f64": (_i, [_i, _vp, _i, _d, C.POINTER(_vp)]),
     "tf_env_set_dynamic": (_i, [_vp, _vp, _i, _f]),
+    "tf_env_build_static_index": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), _f, _i, _f, _i, _vp]),
+    "tf_env_static_index_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_d), C.POINTER(_i), C.POINTER(_d)]),
     "tf_env_build_dynamic_index": (_i, [_vp, _i, _i, C.POINTER(_f), C.POINTER(_f), _f, _i, _vp]),
     "tf_env_dynamic_index_stats": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_d), C.POINTER(_i)]),
     "tf_env_set_voxels": (_i, [_vp, _vp, _i, _i, _i]),

@@ -109,6 +109,20 @@ class Environment:
               "tf_env_set_dynamic")
         return self
 
+    def build_static_index(self, box_lo, box_hi, cell, cap=64, z_cell=1.0, z_cap=32):
+        """Candidate index for the static analytic obstacles (HR or PF rules): same results, a waypoint
+        visits tens of obstacles instead of all N.  See tf_env_build_static_index."""
+        f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])
+        check(lib.tf_env_build_static_index(self._h, f3(box_lo), f3(box_hi), float(cell), int(cap), float(z_cell),
+                                            int(z_cap), _stream()), "tf_env_build_static_index")
+        return self
+
+    def static_index_stats(self):
+        n, over, mean, mx, zmean = C.c_int64(), C.c_int64(), C.c_double(), C.c_int(), C.c_double()
+        check(lib.tf_env_static_index_stats(self._h, C.byref(n), C.byref(over), C.byref(mean), C.byref(mx), C.byref(zmean)),
+              "tf_env_static_index_stats")
+        return dict(lists=n.value, overflowed=over.value, mean_len=mean.value, max_len=mx.value, z_mean_len=zmean.value)
+
     def build_dynamic_index(self, time_slices, box_lo, box_hi, cell, cap=48, band=1):
         """Candidate index for the moving spheres (same results, far fewer sphere tests):
         waypoint i at integer time i < time_slices inside [box_lo, box_hi) only visits the spheres

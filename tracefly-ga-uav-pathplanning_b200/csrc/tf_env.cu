@@ -148,6 +148,122 @@ build_dyn_index_kernel(const float4* __restrict__ dynA, const float4* __restrict
     if (threadIdx.x == 0) count[cellid] = n_list <= cap ? n_list : -1;
 }
 
+// ------------------------------------------------------------------ static candidate index
+// 3-D cells.  For a cell with centre m and half diagonal rho, an obstacle whose (unclamped) distance
+// function f_k is 1-Lipschitz satisfies  max(0, f_k(m) - rho) <= dist_k(p) <= max(0, f_k(m)) + rho  for every
+// point p of the cell; k can be the nearest only if its lower bound does not exceed the smallest upper
+// bound.  Eligible here: HR spheres (f = |m - c|), PF spheres / cubes (f = |m - c| - s) and aabbs (box
+// distance).  PF cylinders measure distance along z only and go to the 1-D index below.  In addition every
+// obstacle whose collision box, grown by half a cell, contains m is listed (it may collide).
+__device__ __forceinline__ float static_f(const EnvDev& e, int semantics, int id, float mx, float my, float mz,
+                                          bool& eligible, float (&half)[3]) {
+    const float4 o = e.tabA[id];
+    const float dx = mx - o.x, dy = my - o.y, dz = mz - o.z;
+    const float d = sqrtf(dx * dx + dy * dy + dz * dz);
+    eligible = true;
+    if (semantics == TF_SEM_HR) {
+        const float R = sqrtf(o.w);
+        half[0] = half[1] = half[2] = R;
+        return d;
+    }
+    const int s_end = e.n_sphere, c_end = s_end + e.n_cube, y_end = c_end + e.n_cyl;
+    if (id < c_end) { half[0] = half[1] = half[2] = o.w; return d - o.w; }
+    if (id < y_end) { half[0] = half[1] = o.w; half[2] = 2.0f * o.w; eligible = false; return 0.0f; }
+    const float4 h = e.tabB[id];
+    half[0] = h.x; half[1] = h.y; half[2] = h.z;
+    const float qx = fmaxf(fabsf(dx) - h.x, 0.0f), qy = fmaxf(fabsf(dy) - h.y, 0.0f), qz = fmaxf(fabsf(dz) - h.z, 0.0f);
+    return sqrtf(qx * qx + qy * qy + qz * qz);
+}
+
+__global__ void __launch_bounds__(128)
+build_static_index_kernel(const __grid_constant__ EnvDev e, int gx, int gy, int gz, float ox, float oy, float oz, float h,
+                          int cap, int32_t* __restrict__ cand, int32_t* __restrict__ count) {
+    __shared__ float red[128];
+    __shared__ int n_list;
+    const size_t c = blockIdx.x;
+    const int ix = (int)(c % gx), iy = (int)((c / gx) % gy), iz = (int)(c / ((size_t)gx * gy));
+    const float mx = ox + ((float)ix + 0.5f) * h, my = oy + ((float)iy + 0.5f) * h, mz = oz + ((float)iz + 0.5f) * h;
+    const float rho = 0.8660254f * h * 1.00001f + 1e-3f, hh = 0.5f * h * 1.00001f + 1e-3f;
+    float ub = INFINITY;
+    for (int k = threadIdx.x; k < e.n; k += 128) {
+        bool el;
+        float half[3];
+        const float f = static_f(e, e.semantics, k, mx, my, mz, el, half);
+        if (el) ub = fminf(ub, fmaxf(f, 0.0f) + rho);
+    }
+    red[threadIdx.x] = ub;
+    if (threadIdx.x == 0) n_list = 0;
+    __syncthreads();
+    for (int off = 64; off > 0; off >>= 1) {
+        if (threadIdx.x < off) red[threadIdx.x] = fminf(red[threadIdx.x], red[threadIdx.x + off]);
+        __syncthreads();
+    }
+    const float lim = red[0] * 1.00001f + 1e-3f;
+    for (int k = threadIdx.x; k < e.n; k += 128) {
+        bool el;
+        float half[3];
+        const float f = static_f(e, e.semantics, k, mx, my, mz, el, half);
+        const float4 o = e.tabA[k];
+        const bool near = el && fmaxf(f - rho, 0.0f) <= lim;
+        const bool coll = fabsf(mx - o.x) <= half[0] + hh && fabsf(my - o.y) <= half[1] + hh && fabsf(mz - o.z) <= half[2] + hh;
+        if (near || coll) {
+            const int pos = atomicAdd(&n_list, 1);
+            if (pos < cap) cand[c * cap + pos] = k;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) count[c] = n_list <= cap ? n_list : -1;
+}
+
+// 1-D z cells for the PF cylinders (distance max(0, |dz| - 2 s), PF:56-57).  If some cylinder's slab
+// contains the whole cell its distance is exactly 0 everywhere in the cell — the global minimum — and
+// that single cylinder is a sufficient candidate; otherwise the lower / upper bound rule as above.
+__global__ void __launch_bounds__(128)
+build_cyl_index_kernel(const __grid_constant__ EnvDev e, int nz, float oz, float hz, int cap,
+                       int32_t* __restrict__ cand, int32_t* __restrict__ count) {
+    __shared__ float red[128];
+    __shared__ int covered[128];
+    __shared__ int n_list;
+    const int c = blockIdx.x;
+    const float mz = oz + ((float)c + 0.5f) * hz;
+    const float dlt = 0.5f * hz * 1.00001f + 1e-3f;
+    const int y0 = e.n_sphere + e.n_cube, y1 = y0 + e.n_cyl;
+    float ub = INFINITY;
+    int cov = 0x7fffffff;
+    for (int k = y0 + threadIdx.x; k < y1; k += 128) {
+        const float4 o = e.tabA[k];
+        const float f = fabsf(mz - o.z) - 2.0f * o.w;
+        ub = fminf(ub, fmaxf(f, 0.0f) + dlt);
+        if (f + dlt <= -1e-3f) cov = min(cov, k);
+    }
+    red[threadIdx.x] = ub;
+    covered[threadIdx.x] = cov;
+    if (threadIdx.x == 0) n_list = 0;
+    __syncthreads();
+    for (int off = 64; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            red[threadIdx.x] = fminf(red[threadIdx.x], red[threadIdx.x + off]);
+            covered[threadIdx.x] = min(covered[threadIdx.x], covered[threadIdx.x + off]);
+        }
+        __syncthreads();
+    }
+    if (covered[0] != 0x7fffffff) {
+        if (threadIdx.x == 0) { cand[(size_t)c * cap] = covered[0]; count[c] = 1; }
+        return;
+    }
+    const float lim = red[0] * 1.00001f + 1e-3f;
+    for (int k = y0 + threadIdx.x; k < y1; k += 128) {
+        const float4 o = e.tabA[k];
+        const float f = fabsf(mz - o.z) - 2.0f * o.w;
+        if (fmaxf(f - dlt, 0.0f) <= lim) {
+            const int pos = atomicAdd(&n_list, 1);
+            if (pos < cap) cand[(size_t)c * cap + pos] = k;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) count[c] = n_list <= cap ? n_list : -1;
+}
+
 // [t][y][x] -> [y][x][t]
 __global__ void hazard_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int nt, size_t nyx) {
     const size_t n = nyx * (size_t)nt;
@@ -204,6 +320,7 @@ static int upload_static(tf_env* env, int semantics, const std::vector<double>& 
     d.semantics = semantics;
     d.n = n;
     d.n_sphere = cnt[0]; d.n_cube = cnt[1]; d.n_cyl = cnt[2]; d.n_aabb = cnt[3];
+    d.n_smem = n;
     d.smax_sc = 0.0f;
     if (semantics == TF_SEM_PF)
         for (int j = 0; j < cnt[0] + cnt[1]; ++j) d.smax_sc = fmaxf(d.smax_sc, A[4 * j + 3]);
@@ -329,6 +446,78 @@ extern "C" int tf_env_dynamic_index_stats(const tf_env* env, int64_t* n_lists, i
     return TF_OK;
 }
 
+extern "C" int tf_env_build_static_index(tf_env* env, const float box_lo[3], const float box_hi[3], float cell, int cap,
+                                         float z_cell, int z_cap, void* stream) {
+    if (!env || !box_lo || !box_hi) return TF_ERR_INVALID;
+    EnvDev& d = env->d;
+    if (d.n <= 0 || (d.semantics != TF_SEM_HR && d.semantics != TF_SEM_PF)) return TF_ERR_INVALID;
+    if (cell <= 0.0f || cap < 1 || cap > 1024 || z_cell <= 0.0f || z_cap < 1 || z_cap > 1024) return TF_ERR_SHAPE;
+    int g[3];
+    for (int a = 0; a < 3; ++a) {
+        if (!(box_hi[a] > box_lo[a])) return TF_ERR_SHAPE;
+        g[a] = (int)ceilf((box_hi[a] - box_lo[a]) / cell);
+        if (g[a] < 1 || g[a] > 512) return TF_ERR_SHAPE;
+    }
+    const size_t ncell = (size_t)g[0] * g[1] * g[2];
+    if (ncell > (size_t)1 << 24) return TF_ERR_SHAPE;
+    const int nz = (int)ceilf((box_hi[2] - box_lo[2]) / z_cell);
+    if (nz < 1 || nz > (1 << 20)) return TF_ERR_SHAPE;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    if (env->sindex_block) { cudaFree(env->sindex_block); env->sindex_block = nullptr; }
+    d.scand = d.scount = d.zcand = d.zcount = nullptr;
+    d.n_smem = d.n;
+    auto r256 = [](size_t b) { return ((b + 255) / 256) * 256; };
+    const size_t b_scount = r256(ncell * 4), b_scand = r256(ncell * (size_t)cap * 4);
+    const size_t b_zcount = r256((size_t)nz * 4), b_zcand = r256((size_t)nz * z_cap * 4);
+    TF_CUDA(cudaMalloc(&env->sindex_block, b_scount + b_scand + b_zcount + b_zcand));
+    char* base = (char*)env->sindex_block;
+    int32_t* scount = (int32_t*)base;
+    int32_t* scand = (int32_t*)(base + b_scount);
+    int32_t* zcount = (int32_t*)(base + b_scount + b_scand);
+    int32_t* zcand = (int32_t*)(base + b_scount + b_scand + b_zcount);
+    cudaStream_t st = (cudaStream_t)stream;
+    build_static_index_kernel<<<(unsigned)ncell, 128, 0, st>>>(d, g[0], g[1], g[2], box_lo[0], box_lo[1], box_lo[2], cell, cap,
+                                                              scand, scount);
+    TF_LAUNCH_CHECK();
+    if (d.semantics == TF_SEM_PF && d.n_cyl > 0) {
+        build_cyl_index_kernel<<<nz, 128, 0, st>>>(d, nz, box_lo[2], z_cell, z_cap, zcand, zcount);
+        TF_LAUNCH_CHECK();
+    }
+    TF_CUDA(cudaStreamSynchronize(st));
+    d.scand = scand; d.scount = scount; d.zcand = zcand; d.zcount = zcount;
+    d.sgx = g[0]; d.sgy = g[1]; d.sgz = g[2]; d.scap = cap;
+    d.sox = box_lo[0]; d.soy = box_lo[1]; d.soz = box_lo[2]; d.sinv_h = 1.0f / cell;
+    d.znz = nz; d.zcap = z_cap; d.zoz = box_lo[2]; d.zinv_h = 1.0f / z_cell;
+    d.n_smem = 0;  // the kernels read the candidate records through L1 / L2
+    return TF_OK;
+}
+
+extern "C" int tf_env_static_index_stats(const tf_env* env, int64_t* n_lists, int64_t* n_overflow, double* mean_len,
+                                         int* max_len, double* z_mean_len) {
+    if (!env || !env->d.scount) return TF_ERR_INVALID;
+    const size_t n = (size_t)env->d.sgx * env->d.sgy * env->d.sgz;
+    std::vector<int32_t> h(n), hz(env->d.znz);
+    TF_CUDA(cudaMemcpy(h.data(), env->d.scount, n * 4, cudaMemcpyDeviceToHost));
+    int64_t over = 0;
+    double sum = 0.0, zsum = 0.0;
+    int mx = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (h[i] < 0) ++over;
+        else { sum += h[i]; if (h[i] > mx) mx = h[i]; }
+    }
+    if (env->d.semantics == TF_SEM_PF && env->d.n_cyl > 0) {
+        TF_CUDA(cudaMemcpy(hz.data(), env->d.zcount, hz.size() * 4, cudaMemcpyDeviceToHost));
+        for (int v : hz) { if (v < 0) ++over; else zsum += v; }
+    }
+    if (n_lists) *n_lists = (int64_t)n;
+    if (n_overflow) *n_overflow = over;
+    if (mean_len) *mean_len = sum / (double)n;
+    if (max_len) *max_len = mx;
+    if (z_mean_len) *z_mean_len = hz.empty() ? 0.0 : zsum / (double)hz.size();
+    return TF_OK;
+}
+
 extern "C" int tf_env_set_voxels(tf_env* env, const uint32_t* bricks_dev, int nx, int ny, int nz) {
     if (!env) return TF_ERR_INVALID;
     if (!bricks_dev) { env->d.bricks = nullptr; return TF_OK; }
@@ -366,6 +555,7 @@ extern "C" int tf_env_destroy(tf_env* env) {
     if (env->dyn_block) cudaFree(env->dyn_block);
     if (env->dindex_block) cudaFree(env->dindex_block);
     if (env->hazard_block) cudaFree(env->hazard_block);
+    if (env->sindex_block) cudaFree(env->sindex_block);
     free(env);
     return TF_OK;
 }

@@ -20,8 +20,8 @@ fitness_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_para
     const Tables tabs{sm.A, sm.B, sm.dA, sm.dB};
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwords = (W + 31) >> 5;
-    const int nchunks = (SEM == TF_SEM_NONE) ? 0 : (e.n + kTableCap - 1) / kTableCap;
-    const bool need_stage = (SEM != TF_SEM_NONE && e.n > 0) || (XF >= 1 && e.n_dyn_smem > 0);
+    const int nchunks = (SEM == TF_SEM_NONE) ? 0 : (e.n_smem + kTableCap - 1) / kTableCap;
+    const bool need_stage = (SEM != TF_SEM_NONE && e.n_smem > 0) || (XF >= 1 && e.n_dyn_smem > 0);
     uint32_t phase = 0;
     bool first_chunk_resident = false;
 
@@ -32,7 +32,7 @@ fitness_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_para
         }
         __syncthreads();
         if (threadIdx.x == 0)
-            stage_chunk(e, sm.A, sm.B, 0, min(e.n, kTableCap), sm.bar, XF >= 1 && e.n_dyn_smem > 0, sm.dA, sm.dB);
+            stage_chunk(e, sm.A, sm.B, 0, min(e.n_smem, kTableCap), sm.bar, XF >= 1 && e.n_dyn_smem > 0, sm.dA, sm.dB);
         mbar_wait(sm.bar, phase);
         phase ^= 1;
         first_chunk_resident = true;
@@ -71,7 +71,7 @@ fitness_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_para
             acc.reset();
             if constexpr (SEM != TF_SEM_NONE) {
                 if (nchunks <= 1) {
-                    eval_static_chunk<SEM, NW>(e, tabs, 0, e.n, cur.x, cur.y, cur.z, acc.hit, acc.best);
+                    eval_static<SEM, NW>(e, tabs, cur.x, cur.y, cur.z, acc.hit, acc.best);
                 } else {
                     // table larger than one chunk: the CTA walks the chunks in lock-step
                     for (int ch = 0; ch < nchunks; ++ch) {
@@ -146,7 +146,7 @@ static int dispatch_sem(const EnvDev& e, const tf_params& prm, const float* pop,
 int check_fitness_args(const tf_env* env, const void* pop, int P, int W, const tf_params* prm, const void* fit) {
     if (!env || !pop || !prm || !fit) return TF_ERR_INVALID;
     if (P < 0 || W < 1 || W > TF_W_MAX) return TF_ERR_SHAPE;
-    if (prm->samples_per_segment > 1 && env->d.n > kTableCap) return TF_ERR_UNSUPPORTED;
+    if (prm->samples_per_segment > 1 && env->d.n_smem > kTableCap) return TF_ERR_UNSUPPORTED;
     if (prm->samples_per_segment > 64) return TF_ERR_SHAPE;
     return TF_OK;
 }

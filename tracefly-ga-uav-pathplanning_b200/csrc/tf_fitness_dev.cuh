@@ -134,6 +134,87 @@ __device__ __forceinline__ void eval_static_chunk(const EnvDev& e, const Tables&
     }
 }
 
+// One obstacle (global table row `id`) against one point — the same arithmetic as the table loops above.
+template <int SEM>
+__device__ __forceinline__ void static_test(const EnvDev& e, int id, float x, float y, float z, bool& hit, float& best) {
+    const float4 o = __ldg(e.tabA + id);
+    const float dx = x - o.x, dy = y - o.y, dz = z - o.z;
+    if constexpr (SEM == TF_SEM_HR) {
+        const float d2 = dist2(dx, dy, dz);
+        hit = hit || (d2 <= o.w);
+        best = fminf(best, d2);
+    } else {
+        const int s_end = e.n_sphere, c_end = s_end + e.n_cube, y_end = c_end + e.n_cyl;
+        if (id < s_end) {
+            const float d2 = dist2(dx, dy, dz);
+            hit = hit || (d2 <= __fmul_rn(o.w, o.w));
+            best = fminf(best, fmaxf(0.0f, __fsub_rn(__fsqrt_rn(d2), o.w)));
+        } else if (id < c_end) {
+            hit = hit || (fabsf(dx) <= o.w && fabsf(dy) <= o.w && fabsf(dz) <= o.w);
+            best = fminf(best, fmaxf(0.0f, __fsub_rn(__fsqrt_rn(dist2(dx, dy, dz)), o.w)));
+        } else if (id < y_end) {
+            const float h = __fmul_rn(2.0f, o.w), az = fabsf(dz);
+            hit = hit || (fabsf(dx) <= o.w && fabsf(dy) <= o.w && az <= h);
+            best = fminf(best, fmaxf(0.0f, __fsub_rn(az, h)));
+        } else {
+            const float4 h = __ldg(e.tabB + id);
+            const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+            hit = hit || (ax <= h.x && ay <= h.y && az <= h.z);
+            const float qx = fmaxf(__fsub_rn(ax, h.x), 0.0f), qy = fmaxf(__fsub_rn(ay, h.y), 0.0f),
+                        qz = fmaxf(__fsub_rn(az, h.z), 0.0f);
+            best = fminf(best, __fsqrt_rn(dist2(qx, qy, qz)));
+        }
+    }
+}
+
+// Static obstacles through the candidate index (tf_env_build_static_index): every point visits the
+// list of its 3-D cell and (PF) of its z cell — supersets of "nearest" and "colliding", so min / or
+// equal the full table loop bit for bit.  Outside the box / overflowed lists: the full loop.
+template <int SEM, int NP>
+__device__ __forceinline__ void eval_static_indexed(const EnvDev& e, const float (&x)[NP], const float (&y)[NP],
+                                                    const float (&z)[NP], uint32_t& hit, float (&best)[NP]) {
+#pragma unroll
+    for (int s = 0; s < NP; ++s) {
+        const int ix = __float2int_rd((x[s] - e.sox) * e.sinv_h), iy = __float2int_rd((y[s] - e.soy) * e.sinv_h),
+                  iz = __float2int_rd((z[s] - e.soz) * e.sinv_h);
+        bool ok = (unsigned)ix < (unsigned)e.sgx && (unsigned)iy < (unsigned)e.sgy && (unsigned)iz < (unsigned)e.sgz;
+        int cnt = -1, zcnt = 0;
+        size_t cell = 0;
+        int zc = 0;
+        if (ok) {
+            cell = ((size_t)iz * e.sgy + iy) * e.sgx + ix;
+            cnt = __ldg(e.scount + cell);
+            if (SEM == TF_SEM_PF && e.n_cyl > 0) {
+                zc = __float2int_rd((z[s] - e.zoz) * e.zinv_h);
+                zcnt = (unsigned)zc < (unsigned)e.znz ? __ldg(e.zcount + zc) : -1;
+            }
+        }
+        bool h = false;
+        float b = best[s];
+        if (cnt >= 0 && zcnt >= 0) {
+            const int32_t* list = e.scand + cell * e.scap;
+            for (int j = 0; j < cnt; ++j) static_test<SEM>(e, __ldg(list + j), x[s], y[s], z[s], h, b);
+            if (SEM == TF_SEM_PF) {
+                const int32_t* zl = e.zcand + (size_t)zc * e.zcap;
+                for (int j = 0; j < zcnt; ++j) static_test<SEM>(e, __ldg(zl + j), x[s], y[s], z[s], h, b);
+            }
+        } else {
+            for (int k = 0; k < e.n; ++k) static_test<SEM>(e, k, x[s], y[s], z[s], h, b);
+        }
+        best[s] = b;
+        hit |= h ? (1u << s) : 0u;
+    }
+}
+
+// Dispatcher used by the single-chunk kernels.
+template <int SEM, int NP>
+__device__ __forceinline__ void eval_static(const EnvDev& e, const Tables& t, const float (&x)[NP],
+                                            const float (&y)[NP], const float (&z)[NP], uint32_t& hit,
+                                            float (&best)[NP]) {
+    if (e.scand != nullptr) eval_static_indexed<SEM, NP>(e, x, y, z, hit, best);
+    else eval_static_chunk<SEM, NP>(e, t, 0, min(e.n, kTableCap), x, y, z, hit, best);
+}
+
 // Moving spheres (extension): HR rules at c(t) = c0 + v t.  Returns min d^2 per point.
 // With a candidate index (tf_env_build_dynamic_index) a point at an integer time slice inside the
 // index box only visits the spheres listed for its cell — a superset of "nearest" and of "colliding"
@@ -259,7 +340,7 @@ __device__ __forceinline__ void eval_point_full(const EnvDev& e, const Tables& t
     float xs[1] = {x}, ys[1] = {y}, zs[1] = {z}, tms[1] = {tm};
     uint32_t hit = 0;
     float best[1] = {INFINITY};
-    eval_static_chunk<SEM, 1>(e, t, 0, min(e.n, kTableCap), xs, ys, zs, hit, best);
+    eval_static<SEM, 1>(e, t, xs, ys, zs, hit, best);
     float dn = (SEM == TF_SEM_HR) ? __fsqrt_rn(best[0]) : best[0];
     if constexpr (XF >= 1) {
         if (e.n_dyn > 0) {
@@ -295,12 +376,12 @@ struct SmemLayout {
     float4 *A, *B, *dA, *dB;
 };
 __host__ __device__ inline size_t smem_bytes_for(const EnvDev& e) {
-    size_t cap = (size_t)(e.n < kTableCap ? e.n : kTableCap);
+    size_t cap = (size_t)(e.n_smem < kTableCap ? e.n_smem : kTableCap);
     return 16 + cap * 16 * (e.n_aabb > 0 ? 2 : 1) + (size_t)e.n_dyn_smem * 32;
 }
 __device__ __forceinline__ SmemLayout carve_smem(const EnvDev& e, unsigned char* smem) {
     SmemLayout s;
-    size_t cap = (size_t)min(e.n, kTableCap);
+    size_t cap = (size_t)min(e.n_smem, kTableCap);
     s.bar = reinterpret_cast<uint64_t*>(smem);
     s.A = reinterpret_cast<float4*>(smem + 16);
     s.B = s.A + (e.n_aabb > 0 ? cap : 0);

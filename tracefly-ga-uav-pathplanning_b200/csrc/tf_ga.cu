@@ -89,14 +89,14 @@ generation_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_p
     const int nwords = (W + 31) >> 5;
     const int ne = min(ga.n_elite, P);
     const bool uniform = ga.crossover == TF_CX_UNIFORM && tape == nullptr;
-    if ((SEM != TF_SEM_NONE && e.n > 0) || (XF >= 1 && e.n_dyn_smem > 0)) {
+    if ((SEM != TF_SEM_NONE && e.n_smem > 0) || (XF >= 1 && e.n_dyn_smem > 0)) {
         if (threadIdx.x == 0) {
             mbar_init(sm.bar, 1);
             fence_mbar_init();
         }
         __syncthreads();
         if (threadIdx.x == 0)
-            stage_chunk(e, sm.A, sm.B, 0, min(e.n, kTableCap), sm.bar, XF >= 1 && e.n_dyn_smem > 0, sm.dA, sm.dB);
+            stage_chunk(e, sm.A, sm.B, 0, min(e.n_smem, kTableCap), sm.bar, XF >= 1 && e.n_dyn_smem > 0, sm.dA, sm.dB);
         mbar_wait(sm.bar, 0);
     }
     const int ntiles = (P + T - 1) / T;
@@ -142,7 +142,7 @@ generation_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_p
             }
             PointAcc<NW, SEM> acc;
             acc.reset();
-            if constexpr (SEM != TF_SEM_NONE) eval_static_chunk<SEM, NW>(e, tabs, 0, e.n, cur.x, cur.y, cur.z, acc.hit, acc.best);
+            if constexpr (SEM != TF_SEM_NONE) eval_static<SEM, NW>(e, tabs, cur.x, cur.y, cur.z, acc.hit, acc.best);
             reduce_chromosome<NW, SEM, VOX, XF>(e, prm, tabs, cur, W, acc, c, sums);
             cur = nxt;
 #pragma unroll
@@ -350,7 +350,7 @@ extern "C" int tf_generation(const tf_env* env, const float* pop_dev, const floa
     if (P < 1 || W < 1 || W > TF_W_MAX) return TF_ERR_SHAPE;
     if (ga->n_elite < 0 || ga->tournament_k < 1 || ga->tournament_k > 32) return TF_ERR_SHAPE;
     if (ga->selection == TF_SEL_TRUNCATION && (ga->n_top < 2 || P < 2)) return TF_ERR_SHAPE;
-    if (env->d.n > kTableCap) return TF_ERR_UNSUPPORTED;  // use tf_ga_step + tf_fitness (same results)
+    if (env->d.n_smem > kTableCap) return TF_ERR_UNSUPPORTED;  // use tf_ga_step + tf_fitness (same results)
     if (params->samples_per_segment > 64) return TF_ERR_SHAPE;
     int rc = ensure_device();
     if (rc != TF_OK) return rc;

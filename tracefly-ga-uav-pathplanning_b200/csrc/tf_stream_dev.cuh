@@ -128,12 +128,12 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 #pragma unroll
         for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);
     }
-    if ((SEM != TF_SEM_NONE && e.n > 0) || (XF >= 1 && e.n_dyn_smem > 0)) {
+    if ((SEM != TF_SEM_NONE && e.n_smem > 0) || (XF >= 1 && e.n_dyn_smem > 0)) {
         if (threadIdx.x == 0) mbar_init(sm.bar, 1);
         fence_mbar_init();
         __syncthreads();
         if (threadIdx.x == 0)
-            stage_chunk(e, sm.A, sm.B, 0, min(e.n, kTableCap), sm.bar, XF >= 1 && e.n_dyn_smem > 0, sm.dA, sm.dB);
+            stage_chunk(e, sm.A, sm.B, 0, min(e.n_smem, kTableCap), sm.bar, XF >= 1 && e.n_dyn_smem > 0, sm.dA, sm.dB);
         mbar_wait(sm.bar, 0);
     } else {
         fence_mbar_init();
@@ -243,7 +243,7 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
             }
             PointAcc<NW, SEM> acc;
             acc.reset();
-            if constexpr (SEM != TF_SEM_NONE) eval_static_chunk<SEM, NW>(e, tabs, 0, e.n, cur.x, cur.y, cur.z, acc.hit, acc.best);
+            if constexpr (SEM != TF_SEM_NONE) eval_static<SEM, NW>(e, tabs, cur.x, cur.y, cur.z, acc.hit, acc.best);
             reduce_fullw<NW, SEM, VOX, XF>(e, prm, tabs, cur, prev, v0w, v0m, acc, c, sums);
             __syncwarp();  // every lane is done with this ring slot: refill it
             if (c + kStages < cnt) issue(c + kStages, head);
@@ -311,7 +311,7 @@ static int stream_dispatch(const StreamArgs& a) {
 
 // Host-side eligibility: full-length chromosomes, single table chunk, contiguous parent pieces.
 inline bool stream_eligible(const EnvDev& e, int W, bool uniform_mask) {
-    if ((W != 32 && W != 64) || uniform_mask || e.n > kTableCap) return false;
+    if ((W != 32 && W != 64) || uniform_mask || e.n_smem > kTableCap) return false;
     return stream_smem_bytes(e, W) <= 200 * 1024;
 }
 
