@@ -33,15 +33,14 @@ from . import _lib as L
 from . import batched as B
 
 
-# ========================
-# Utility: Read Obstacle Data   (HR:10-15)
-# ========================
 def load_obstacles_from_json(filepath: str) -> List[dict]:
-    if not os.path.exists(filepath):
+    """detected_objects.json -> list of {"position": [...], "size"?: s} (HR:10-15); a missing file means
+    an empty world."""
+    try:
+        with open(filepath, "r") as handle:
+            return json.load(handle).get("detected_objects", [])
+    except FileNotFoundError:
         return []
-    with open(filepath, "r") as f:
-        data = json.load(f)
-    return data.get("detected_objects", [])
 
 
 def _env_for(obstacles, safety_radius=2.0):
@@ -77,17 +76,14 @@ def distance_to_nearest_obstacle(point, obstacles):
     return float(dn[0])
 
 
-# ========================
-# Genetic Algorithm Components
-# ========================
 class Path:
     def __init__(self, waypoints: List[Tuple[int, int, int]]):
         self.waypoints = waypoints
         self.fitness = 0
 
-    def is_turning(self, i):  # HR:38-40
-        return (self.waypoints[i][0] != self.waypoints[i - 1][0] or
-                self.waypoints[i][1] != self.waypoints[i - 1][1])
+    def is_turning(self, i):  # HR:38-40: heading change in the horizontal plane
+        here, before = self.waypoints[i], self.waypoints[i - 1]
+        return tuple(here[:2]) != tuple(before[:2])
 
     def calculate_fitness(self, obstacles):  # HR:42-59
         env = obstacles if isinstance(obstacles, B.Environment) else _env_for(obstacles)
@@ -127,22 +123,19 @@ class HRMAGAGenerator:
         init = self.generate_initial_path(start, end)
         return [Path(list(init)) for _ in range(self.population_size)]
 
-    # ---- HR:85-89 (host objects in, host objects out; draws from np.random like the reference)
+    # ---- HR:85-99 for single Path objects (evolve() does the same on the device for the whole
+    #      population); both draw from np.random in the reference's order
     def crossover(self, p1, p2):
-        cp = np.random.randint(1, min(len(p1.waypoints), len(p2.waypoints)) - 1)
-        child1_wp = p1.waypoints[:cp] + p2.waypoints[cp:]
-        child2_wp = p2.waypoints[:cp] + p1.waypoints[cp:]
-        return Path(child1_wp), Path(child2_wp)
+        a, b = p1.waypoints, p2.waypoints
+        cut = np.random.randint(1, min(len(a), len(b)) - 1)
+        return Path(a[:cut] + b[cut:]), Path(b[:cut] + a[cut:])
 
-    # ---- HR:91-99
     def mutate(self, path):
-        if len(path.waypoints) == 0:
-            return path
-        if np.random.rand() < self.mutation_rate:
-            mp = np.random.randint(1, len(path.waypoints) - 1)
-            dx, dy, dz = np.random.choice([-1, 0, 1], 3)
-            w = path.waypoints[mp]
-            path.waypoints[mp] = (w[0] + int(dx), w[1] + int(dy), w[2] + int(dz))
+        n = len(path.waypoints)
+        if n and np.random.rand() < self.mutation_rate:
+            at = np.random.randint(1, n - 1)
+            delta = np.random.choice([-1, 0, 1], 3)
+            path.waypoints[at] = tuple(v + int(d) for v, d in zip(path.waypoints[at], delta))
         return path
 
     # ---- the np.random draws of one generation, in the reference's order (HR:117-120)
@@ -210,29 +203,22 @@ class HRMAGAGenerator:
         return generate_local_path(start_point, end_point, planner=self)
 
 
-# ========================
-# Wrapper Method to Run HR-MAGA for Waypoints   (HR:138-160)
-# ========================
+DETECTIONS_FILE = "data/detected_objects.json"   # written by the LiDAR module (HR:139)
+RESULT_FILE = "data/ga_path_output.json"         # read by the mission loop / compression stage (HR:140)
+
+
 def generate_local_path(start_point, end_point, planner=None):
-    lidar_file = "data/detected_objects.json"
-    output_file = "data/ga_path_output.json"
-    os.makedirs("data", exist_ok=True)
-
-    obstacles = load_obstacles_from_json(lidar_file)
-    planner = planner or HRMAGAGenerator()
-    best_path = planner.evolve(start_point, end_point, obstacles)
-
-    if best_path:
-        output_data = {
-            "path": best_path,
-            "start": start_point,
-            "end": end_point,
-            "timestamp": datetime.utcnow().isoformat()  # noqa: same call as HR:152,
-        }
-        with open(output_file, "w") as f:
-            json.dump(output_data, f, indent=2)
-        print(f"✅ Path saved to {output_file}")
-    else:
+    """HR:138-160: plan one mission segment.  Obstacles are re-read from DETECTIONS_FILE on every call
+    (the reference's notion of a dynamic world); a non-empty result is written to RESULT_FILE with the
+    keys path / start / end / timestamp."""
+    os.makedirs(os.path.dirname(RESULT_FILE), exist_ok=True)
+    planner = planner if planner is not None else HRMAGAGenerator()
+    best_path = planner.evolve(start_point, end_point, load_obstacles_from_json(DETECTIONS_FILE))
+    if not best_path:
         print("❌ No path generated due to emergency stop or invalid configuration.")
-
+        return best_path
+    record = dict(path=best_path, start=start_point, end=end_point, timestamp=datetime.utcnow().isoformat())
+    with open(RESULT_FILE, "w") as handle:
+        json.dump(record, handle, indent=2)
+    print(f"✅ Path saved to {RESULT_FILE}")
     return best_path
