@@ -123,6 +123,11 @@ int64_t tf_voxel_grid_bytes(int nx, int ny, int nz);
  * lattice point (x,y,z) collides.  obs_dev: tf_obstacle[n] on the DEVICE. */
 int tf_voxelize(int semantics, const tf_obstacle* obs_dev, int n, float safety_radius,
                 uint32_t* bricks_dev, int nx, int ny, int nz, void* stream);
+/* LiDAR point cloud f32[n][4] (x, y, z, pad) on the device -> occupancy bits: each point marks voxel
+ * floor((p - origin) / voxel_size) — the assignment of downsample_lidar (lidar_compression.py:242-246),
+ * which truncates toward zero: identical for every point inside the grid (non-negative offsets). */
+int tf_voxelize_points(const float* points_dev, int64_t n, const float origin[3], float voxel_size,
+                       uint32_t* bricks_dev, int nx, int ny, int nz, void* stream);
 /* Linear bit grid (bit index x + nx*(y + ny*z), LSB first in u32 words) -> brick layout. */
 int tf_voxel_pack_linear(const uint32_t* linear_dev, uint32_t* bricks_dev, int nx, int ny, int nz, void* stream);
 

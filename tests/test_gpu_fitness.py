@@ -251,3 +251,18 @@ def test_static_index_equals_full_table_loop(tf, sem, W):
         assert torch.equal(g0[0], g1[0]) and torch.equal(g0[1], g1[1]) and torch.equal(g0[2], g1[2])
     st = B.Environment(semc, table, 2.0).build_static_index((0, 0, 0), (world,) * 3, 8.0, 96).static_index_stats()
     assert st["overflowed"] == 0 and st["mean_len"] < 40
+
+
+def test_voxelize_points(tf):
+    """LiDAR points -> occupancy bits (lidar_compression.py:242-246 voxel assignment), vs numpy."""
+    torch, L, B = tf
+    rng = np.random.default_rng(4)
+    dims, origin, vs = (64, 32, 16), (-3.0, 2.0, 0.5), 0.25
+    pts = rng.uniform(-5, 15, size=(20000, 4)).astype(np.float32)
+    got = as_u32(B.voxelize_points(torch.from_numpy(pts).cuda(), dims, origin, vs))
+    idx = np.floor((pts[:, :3] - np.array(origin, np.float32)) * np.float32(1.0 / vs)).astype(np.int64)
+    ok = np.all((idx >= 0) & (idx < np.array(dims)), axis=1)
+    lin = np.zeros(dims[0] * dims[1] * dims[2] // 32, np.uint32)
+    b = idx[ok, 0] + dims[0] * (idx[ok, 1] + dims[1] * idx[ok, 2])
+    np.bitwise_or.at(lin, b >> 5, (np.uint32(1) << (b & 31).astype(np.uint32)))
+    assert ok.sum() > 1000 and np.array_equal(got, O.voxel_pack_linear(lin, *dims))

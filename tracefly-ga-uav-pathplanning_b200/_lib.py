@@ -55,6 +55,7 @@ _SIGS = {
     "tf_env_destroy": (_i, [_vp]),
     "tf_voxel_grid_bytes": (_i64, [_i, _i, _i]),
     "tf_voxelize": (_i, [_i, _vp, _i, _f, _vp, _i, _i, _i, _vp]),
+    "tf_voxelize_points": (_i, [_vp, _i64, C.POINTER(_f), _f, _vp, _i, _i, _i, _vp]),
     "tf_voxel_pack_linear": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "tf_params_default": (None, [C.POINTER(Params)]),
     "tf_ga_params_default": (None, [C.POINTER(GaParams)]),

@@ -210,6 +210,19 @@ def voxelize(table, dims, semantics=L.SEM_PF, safety_radius=0.0, out=None):
     return out
 
 
+def voxelize_points(points, dims, origin=(0.0, 0.0, 0.0), voxel_size=1.0, out=None):
+    """LiDAR point cloud (CUDA tensor f32[n, 4]) -> brick-layout occupancy grid; may be called repeatedly
+    on the same grid to accumulate scans."""
+    _chk_tensor(points, torch.float32, "points", 2)
+    nx, ny, nz = dims
+    if out is None:
+        out = torch.zeros(voxel_grid_words(nx, ny, nz), dtype=torch.int32, device=points.device)
+    o = (C.c_float * 3)(*[float(v) for v in origin])
+    check(lib.tf_voxelize_points(_ptr(points), points.shape[0], o, float(voxel_size), _ptr(out), nx, ny, nz, _stream()),
+          "tf_voxelize_points")
+    return out
+
+
 def voxel_pack_linear(linear, dims):
     """linear: int32 CUDA tensor, bit index x + nx*(y + ny*z) -> brick layout."""
     nx, ny, nz = dims

@@ -85,3 +85,37 @@ extern "C" int tf_fitness_gae(const float* pop_dev, const int32_t* lens_dev, int
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// LiDAR point cloud -> bit-packed occupancy: every point marks the voxel that
+// contains it, floor((p - origin) / voxel_size) — the voxel assignment of `downsample_lidar`
+// (UAV_Navigation/data_compression/lidar_compression.py:242-246), kept as occupancy bits in the
+// brick layout the fitness kernels probe.  Points outside the grid are ignored.
+namespace tf {
+__global__ void voxelize_points_kernel(const float4* __restrict__ pts, int64_t n, float ox, float oy, float oz,
+                                       float inv_voxel, uint32_t* __restrict__ bricks, int nx, int ny, int nz) {
+    const int nbx = nx >> 3, nby = ny >> 3;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 p = pts[i];
+        const int x = __float2int_rd(__fmul_rn(p.x - ox, inv_voxel)), y = __float2int_rd(__fmul_rn(p.y - oy, inv_voxel)),
+                  z = __float2int_rd(__fmul_rn(p.z - oz, inv_voxel));
+        if ((unsigned)x >= (unsigned)nx || (unsigned)y >= (unsigned)ny || (unsigned)z >= (unsigned)nz) continue;
+        const size_t brick = (size_t)(x >> 3) + (size_t)nbx * ((size_t)(y >> 3) + (size_t)nby * (size_t)(z >> 3));
+        atomicOr(bricks + brick * 16 + ((z & 7) * 2 + ((y & 7) >> 2)), 1u << (((y & 3) << 3) | (x & 7)));
+    }
+}
+}  // namespace tf
+
+extern "C" int tf_voxelize_points(const float* points_dev, int64_t n, const float origin[3], float voxel_size,
+                                  uint32_t* bricks_dev, int nx, int ny, int nz, void* stream) {
+    if (!bricks_dev || !origin || (n > 0 && !points_dev) || n < 0) return TF_ERR_INVALID;
+    if (!(voxel_size > 0.0f) || tf_voxel_grid_bytes(nx, ny, nz) < 0) return TF_ERR_SHAPE;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    if (n == 0) return TF_OK;
+    const int64_t want = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
+    tf::voxelize_points_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(points_dev), n, origin[0], origin[1], origin[2], 1.0f / voxel_size, bricks_dev, nx, ny, nz);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
