@@ -13,7 +13,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libtracefly_b200.so")
 SOURCES = ["tf_env.cu", "tf_fitness.cu", "tf_rank.cu", "tf_ga.cu", "tf_io.cu"]
-HEADERS = ["tf_common.cuh", "tf_fitness_dev.cuh", "tf_ga_dev.cuh", "tf_stream_dev.cuh", "../../include/tracefly_b200.h"]
+HEADERS = ["tf_common.cuh", "tf_fitness_dev.cuh", "tf_ga_dev.cuh", "tf_stream_dev.cuh", "tf_stream_host.cuh",
+           "tf_fitness_kernels.cuh", "tf_generation_kernels.cuh", "tf_inst.cu", "../../include/tracefly_b200.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -39,23 +40,40 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+# tf_inst.cu is compiled once per (kernel family, waypoints-per-lane): the template instantiations
+# (hundreds of kernels) then build in parallel instead of inside two giant translation units.
+INSTANCES = [(kind, nw) for kind in (0, 1) for nw in (1, 2, 4, 8)] + [(kind, nw) for kind in (2, 3) for nw in (1, 2)]
+MAX_JOBS = max(1, min(8, os.cpu_count() or 1))
+
+
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
-    objs = []
-    procs = []
+    jobs = []
     for src in SOURCES:
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
-    for src, p in procs:
-        out, _ = p.communicate()
-        if verbose or p.returncode != 0:
+        jobs.append((src, obj, []))
+    for kind, nw in INSTANCES:
+        obj = os.path.join(OUT_DIR, f"tf_inst_k{kind}_nw{nw}.o")
+        jobs.append(("tf_inst.cu", obj, [f"-DTF_INST_KIND={kind}", f"-DTF_INST_NW={nw}"]))
+    # longest jobs first (the stream / generation instantiations), at most MAX_JOBS compilers at a time
+    jobs.sort(key=lambda j: (j[0] != "tf_inst.cu", j[1]))
+    objs = [j[1] for j in jobs]
+    running, pending = [], list(jobs)
+    while pending or running:
+        while pending and len(running) < MAX_JOBS:
+            src, obj, defs = pending.pop(0)
+            cmd = [nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+            running.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        src, obj, proc = running.pop(0)
+        out, _ = proc.communicate()
+        if verbose or proc.returncode != 0:
             sys.stderr.write(out)
-        if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}")
+        if proc.returncode != 0:
+            for _, _, p in running:
+                p.kill()
+            raise RuntimeError(f"nvcc failed on {src} -> {os.path.basename(obj)}")
     cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     subprocess.check_call(cmd)
     return LIB

@@ -1,147 +1,18 @@
 // tf_fitness.cu — tf_fitness (FP32, one warp per chromosome) and tf_fitness_f64
 // (reference-order float64, one thread per chromosome).
 #include "tf_fitness_dev.cuh"
-#include "tf_stream_dev.cuh"
+#include "tf_stream_host.cuh"
 
 namespace tf {
 
-// ------------------------------------------------------------------------------------------
-// FP32 throughput kernel.  Persistent grid; every CTA stages the obstacle table into shared
-// memory with one TMA bulk copy; each of its 8 warps then takes TILES of 32 chromosomes:
-// phase B streams one chromosome at a time (coalesced float4 loads, L1 no-allocate, next
-// chromosome prefetched) and reduces it across the warp, phase C scores 32 chromosomes at once.
-template <int NW, int SEM, bool VOX, int XF>
-__global__ void __launch_bounds__(kBlockThreads)
-fitness_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
-               const float4* __restrict__ pop, const int32_t* __restrict__ lens, int P, int W, int T,
-               float* __restrict__ fit, uint32_t* __restrict__ coll) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout sm = carve_smem(e, smem);
-    const Tables tabs{sm.A, sm.B, sm.dA, sm.dB};
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwords = (W + 31) >> 5;
-    const int nchunks = (SEM == TF_SEM_NONE) ? 0 : (e.n_smem + kTableCap - 1) / kTableCap;
-    const bool need_stage = (SEM != TF_SEM_NONE && e.n_smem > 0) || (XF >= 1 && e.n_dyn_smem > 0);
-    uint32_t phase = 0;
-    bool first_chunk_resident = false;
-
-    if (need_stage) {
-        if (threadIdx.x == 0) {
-            mbar_init(sm.bar, 1);
-            fence_mbar_init();
-        }
-        __syncthreads();
-        if (threadIdx.x == 0)
-            stage_chunk(e, sm.A, sm.B, 0, min(e.n_smem, kTableCap), sm.bar, XF >= 1 && e.n_dyn_smem > 0, sm.dA, sm.dB);
-        mbar_wait(sm.bar, phase);
-        phase ^= 1;
-        first_chunk_resident = true;
-    }
-
-    const int ntiles = (P + T - 1) / T;  // T = chromosomes per tile (host picks 32 unless P is small)
-    // CTA-uniform trip count (the multi-chunk path synchronises the whole CTA per chunk)
-    for (int tbase = blockIdx.x * kWarpsPerBlock; tbase < ntiles; tbase += gridDim.x * kWarpsPerBlock) {
-        const int tile = tbase + warp;
-        const int p0 = tile * T;
-        const int cnt = max(0, min(T, P - p0));  // chromosomes of this warp's tile (0: idle warp)
-        const int myL = (lane < cnt) ? (lens ? min(lens[p0 + lane], W) : W) : 0;
-        TileSums<NW> sums;
-        sums.reset();
-
-        auto load = [&](int c, Lanes<NW>& dst) {
-            const int L = __shfl_sync(0xffffffffu, myL, c);
-            const float4* row = pop + (size_t)(p0 + (c < cnt ? c : 0)) * W;
-#pragma unroll
-            for (int s = 0; s < NW; ++s) {
-                const int k = lane + 32 * s;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k < L) v = ldg_stream(row + k);
-                dst.x[s] = v.x; dst.y[s] = v.y; dst.z[s] = v.z;
-            }
-            return L;
-        };
-
-        Lanes<NW> cur, nxt;
-        int Lc = load(0, cur), Ln = 0;
-        const int climit = (nchunks > 1) ? T : cnt;  // multi-chunk: every warp walks all T (syncs inside)
-#pragma unroll 1
-        for (int c = 0; c < climit; ++c) {
-            if (c + 1 < climit) Ln = load(c + 1, nxt);
-            PointAcc<NW, SEM> acc;
-            acc.reset();
-            if constexpr (SEM != TF_SEM_NONE) {
-                if (nchunks <= 1) {
-                    eval_static<SEM, NW>(e, tabs, cur.x, cur.y, cur.z, acc.hit, acc.best);
-                } else {
-                    // table larger than one chunk: the CTA walks the chunks in lock-step
-                    for (int ch = 0; ch < nchunks; ++ch) {
-                        const int row0 = ch * kTableCap, n = min(kTableCap, e.n - row0);
-                        if (!(ch == 0 && first_chunk_resident)) {
-                            __syncthreads();  // everyone is done reading the previous chunk
-                            if (threadIdx.x == 0) stage_chunk(e, sm.A, sm.B, row0, n, sm.bar, false, sm.dA, sm.dB);
-                            mbar_wait(sm.bar, phase);
-                            phase ^= 1;
-                        }
-                        first_chunk_resident = false;
-                        eval_static_chunk<SEM, NW>(e, tabs, row0, n, cur.x, cur.y, cur.z, acc.hit, acc.best);
-                    }
-                }
-            }
-            reduce_chromosome<NW, SEM, VOX, XF>(e, prm, tabs, cur, Lc, acc, c, sums);
-            cur = nxt;
-            Lc = Ln;
-        }
-        // phase C: lane = chromosome
-        if (lane < cnt) {
-            const int p = p0 + lane;
-            fit[p] = combine_fitness<NW, XF>(e, prm, sums);
-            if (coll) {
-#pragma unroll
-                for (int s = 0; s < NW; ++s)
-                    if (s < nwords) coll[(size_t)p * nwords + s] = sums.cw[s];
-            }
-        }
-    }
-}
-
-template <int NW, int SEM, bool VOX, int XF>
-static int launch_fitness(const EnvDev& e, const tf_params& prm, const float* pop, const int32_t* lens, int P, int W,
-                          float* fit, uint32_t* coll, cudaStream_t st) {
-    auto kern = fitness_kernel<NW, SEM, VOX, XF>;
-    size_t smem = smem_bytes_for(e);
-    if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int T = tile_size_for(P);
-    const int ntiles = (P + T - 1) / T;
-    int grid = min((ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
-    kern<<<grid, kBlockThreads, smem, st>>>(e, prm, reinterpret_cast<const float4*>(pop), lens, P, W, T, fit, coll);
-    TF_LAUNCH_CHECK();
-    return TF_OK;
-}
-
-template <int NW, int SEM>
-static int dispatch_flags(const EnvDev& e, const tf_params& prm, const float* pop, const int32_t* lens, int P, int W,
-                          float* fit, uint32_t* coll, cudaStream_t st) {
-    const bool vox = e.bricks != nullptr;
-    const int xf = prm.samples_per_segment > 1 ? 2 : ((e.n_dyn > 0 || e.hazard != nullptr) ? 1 : 0);
-    if (vox) {
-        if (xf == 2) return launch_fitness<NW, SEM, true, 2>(e, prm, pop, lens, P, W, fit, coll, st);
-        if (xf == 1) return launch_fitness<NW, SEM, true, 1>(e, prm, pop, lens, P, W, fit, coll, st);
-        return launch_fitness<NW, SEM, true, 0>(e, prm, pop, lens, P, W, fit, coll, st);
-    }
-    if (xf == 2) return launch_fitness<NW, SEM, false, 2>(e, prm, pop, lens, P, W, fit, coll, st);
-    if (xf == 1) return launch_fitness<NW, SEM, false, 1>(e, prm, pop, lens, P, W, fit, coll, st);
-    return launch_fitness<NW, SEM, false, 0>(e, prm, pop, lens, P, W, fit, coll, st);
-}
-
-template <int NW>
-static int dispatch_sem(const EnvDev& e, const tf_params& prm, const float* pop, const int32_t* lens, int P, int W,
-                        float* fit, uint32_t* coll, cudaStream_t st) {
-    switch (e.n > 0 ? e.semantics : TF_SEM_NONE) {
-    case TF_SEM_HR: return dispatch_flags<NW, TF_SEM_HR>(e, prm, pop, lens, P, W, fit, coll, st);
-    case TF_SEM_PF: return dispatch_flags<NW, TF_SEM_PF>(e, prm, pop, lens, P, W, fit, coll, st);
-    default: return dispatch_flags<NW, TF_SEM_NONE>(e, prm, pop, lens, P, W, fit, coll, st);
-    }
-}
+// per-NW instantiations live in tf_inst.cu (compiled once per NW)
+int fitness_lsu_nw1(const EnvDev&, const tf_params&, const float*, const int32_t*, int, int, float*, uint32_t*, cudaStream_t);
+int fitness_lsu_nw2(const EnvDev&, const tf_params&, const float*, const int32_t*, int, int, float*, uint32_t*, cudaStream_t);
+int fitness_lsu_nw4(const EnvDev&, const tf_params&, const float*, const int32_t*, int, int, float*, uint32_t*, cudaStream_t);
+int fitness_lsu_nw8(const EnvDev&, const tf_params&, const float*, const int32_t*, int, int, float*, uint32_t*, cudaStream_t);
+int fitness_stream_nw1(const StreamArgs&);
+int fitness_stream_nw2(const StreamArgs&);
+static int fitness_stream(const StreamArgs& a) { return a.W == 32 ? fitness_stream_nw1(a) : fitness_stream_nw2(a); }
 
 int check_fitness_args(const tf_env* env, const void* pop, int P, int W, const tf_params* prm, const void* fit) {
     if (!env || !pop || !prm || !fit) return TF_ERR_INVALID;
@@ -272,18 +143,18 @@ extern "C" int tf_fitness(const tf_env* env, const float* pop_dev, const int32_t
     if ((rc = ensure_device()) != TF_OK) return rc;
     if (P == 0) return TF_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (lens_dev == nullptr && stream_eligible(env->d, W, false) && !g_disable_stream) {
+    if (lens_dev == nullptr && stream_eligible(env->d, *params, W, false) && !g_disable_stream) {
         tf_ga_params ga_unused;
         tf_ga_params_default(&ga_unused);
         StreamArgs sa{&env->d, params, &ga_unused, pop_dev, nullptr, nullptr, nullptr, 0, 0, P, W,
                       nullptr, fit_dev, coll_dev, nullptr, nullptr, st};
-        return stream_dispatch<false>(sa);
+        return fitness_stream(sa);
     }
     const int nw = (W + 31) / 32;
-    if (nw <= 1) return dispatch_sem<1>(env->d, *params, pop_dev, lens_dev, P, W, fit_dev, coll_dev, st);
-    if (nw <= 2) return dispatch_sem<2>(env->d, *params, pop_dev, lens_dev, P, W, fit_dev, coll_dev, st);
-    if (nw <= 4) return dispatch_sem<4>(env->d, *params, pop_dev, lens_dev, P, W, fit_dev, coll_dev, st);
-    return dispatch_sem<8>(env->d, *params, pop_dev, lens_dev, P, W, fit_dev, coll_dev, st);
+    if (nw <= 1) return fitness_lsu_nw1(env->d, *params, pop_dev, lens_dev, P, W, fit_dev, coll_dev, st);
+    if (nw <= 2) return fitness_lsu_nw2(env->d, *params, pop_dev, lens_dev, P, W, fit_dev, coll_dev, st);
+    if (nw <= 4) return fitness_lsu_nw4(env->d, *params, pop_dev, lens_dev, P, W, fit_dev, coll_dev, st);
+    return fitness_lsu_nw8(env->d, *params, pop_dev, lens_dev, P, W, fit_dev, coll_dev, st);
 }
 
 extern "C" int tf_fitness_f64(const tf_env* env, const double* pop64_dev, const int32_t* lens_dev, int P, int W,

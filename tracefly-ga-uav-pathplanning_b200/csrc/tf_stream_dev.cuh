@@ -15,15 +15,9 @@
 #pragma once
 #include "tf_fitness_dev.cuh"
 #include "tf_ga_dev.cuh"
+#include "tf_stream_host.cuh"
 
 namespace tf {
-
-constexpr int kStages = 6;
-
-__host__ __device__ inline size_t stream_smem_bytes(const EnvDev& e, int W) {
-    size_t tables = (smem_bytes_for(e) + 127) & ~(size_t)127;
-    return tables + (size_t)kWarpsPerBlock * kStages * W * 16 + (size_t)kWarpsPerBlock * kStages * 8;
-}
 
 // Score bookkeeping of one full-length chromosome whose waypoints sit in shared memory.
 template <int NW, int SEM, bool VOX, int XF>
@@ -263,11 +257,6 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
     }
 }
 
-struct StreamArgs {
-    const EnvDev* e; const tf_params* prm; const tf_ga_params* ga; const float* pop; const float* fit;
-    const int32_t* top_idx; const tf_draw* tape; uint64_t seed; uint32_t gen; int P, W;
-    float* next; float* out_fit; uint32_t* out_coll; int32_t* sel; int32_t* cpo; cudaStream_t st;
-};
 
 template <int NW, int SEM, bool VOX, int XF, bool GA>
 static int launch_stream(const StreamArgs& a) {
@@ -285,16 +274,11 @@ static int launch_stream(const StreamArgs& a) {
 }
 template <int NW, int SEM, bool GA>
 static int stream_flags(const StreamArgs& a) {
+    // XF 2 (samples per segment > 1) is served by the LSU-path kernels only (stream_eligible)
     const bool vox = a.e->bricks != nullptr;
-    const int xf = a.prm->samples_per_segment > 1 ? 2 : ((a.e->n_dyn > 0 || a.e->hazard != nullptr) ? 1 : 0);
-    if (vox) {
-        if (xf == 2) return launch_stream<NW, SEM, true, 2, GA>(a);
-        if (xf == 1) return launch_stream<NW, SEM, true, 1, GA>(a);
-        return launch_stream<NW, SEM, true, 0, GA>(a);
-    }
-    if (xf == 2) return launch_stream<NW, SEM, false, 2, GA>(a);
-    if (xf == 1) return launch_stream<NW, SEM, false, 1, GA>(a);
-    return launch_stream<NW, SEM, false, 0, GA>(a);
+    const bool xf1 = a.e->n_dyn > 0 || a.e->hazard != nullptr;
+    if (vox) return xf1 ? launch_stream<NW, SEM, true, 1, GA>(a) : launch_stream<NW, SEM, true, 0, GA>(a);
+    return xf1 ? launch_stream<NW, SEM, false, 1, GA>(a) : launch_stream<NW, SEM, false, 0, GA>(a);
 }
 template <int NW, bool GA>
 static int stream_sem(const StreamArgs& a) {
@@ -304,15 +288,4 @@ static int stream_sem(const StreamArgs& a) {
     default: return stream_flags<NW, TF_SEM_NONE, GA>(a);
     }
 }
-template <bool GA>
-static int stream_dispatch(const StreamArgs& a) {
-    return a.W == 32 ? stream_sem<1, GA>(a) : stream_sem<2, GA>(a);
-}
-
-// Host-side eligibility: full-length chromosomes, single table chunk, contiguous parent pieces.
-inline bool stream_eligible(const EnvDev& e, int W, bool uniform_mask) {
-    if ((W != 32 && W != 64) || uniform_mask || e.n_smem > kTableCap) return false;
-    return stream_smem_bytes(e, W) <= 200 * 1024;
-}
-
 }  // namespace tf

@@ -1,0 +1,34 @@
+// tf_stream_host.cuh — argument packs and host-side eligibility of the TMA-staged stream kernels and the
+// LSU-path generation kernel (no kernel templates here: those are instantiated in tf_inst.cu).
+#pragma once
+#include "tf_fitness_dev.cuh"
+
+namespace tf {
+
+constexpr int kStages = 6;
+
+__host__ __device__ inline size_t stream_smem_bytes(const EnvDev& e, int W) {
+    size_t tables = (smem_bytes_for(e) + 127) & ~(size_t)127;
+    return tables + (size_t)kWarpsPerBlock * kStages * W * 16 + (size_t)kWarpsPerBlock * kStages * 8;
+}
+
+struct StreamArgs {
+    const EnvDev* e; const tf_params* prm; const tf_ga_params* ga; const float* pop; const float* fit;
+    const int32_t* top_idx; const tf_draw* tape; uint64_t seed; uint32_t gen; int P, W;
+    float* next; float* out_fit; uint32_t* out_coll; int32_t* sel; int32_t* cpo; cudaStream_t st;
+};
+
+struct GenArgs {
+    const EnvDev* e; const tf_params* prm; const tf_ga_params* ga; const float* pop; const float* fit;
+    const int32_t* top_idx; const tf_draw* tape; uint64_t seed; uint32_t gen; int P, W;
+    float* next; float* next_fit; uint32_t* next_coll; int32_t* sel; int32_t* cpo; cudaStream_t st;
+};
+
+// Host-side eligibility: full-length chromosomes, single table chunk, contiguous parent pieces.
+inline bool stream_eligible(const EnvDev& e, const tf_params& prm, int W, bool uniform_mask) {
+    if (prm.samples_per_segment > 1) return false;
+    if ((W != 32 && W != 64) || uniform_mask || e.n_smem > kTableCap) return false;
+    return stream_smem_bytes(e, W) <= 200 * 1024;
+}
+
+}  // namespace tf
