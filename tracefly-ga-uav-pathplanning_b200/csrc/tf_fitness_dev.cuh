@@ -297,14 +297,14 @@ struct VoxRegs {
     uint32_t word[NW], mask[NW];
 };
 template <int NW>
-__device__ __forceinline__ void voxel_prefetch(const EnvDev& e, const Lanes<NW>& p, VoxRegs<NW>& v) {
+__device__ __forceinline__ void voxel_prefetch(const EnvDev& e, const Lanes<NW>& p, VoxRegs<NW>& v, uint64_t keep_policy) {
 #pragma unroll
     for (int s = 0; s < NW; ++s) {
         const int ix = __float2int_rd(p.x[s]), iy = __float2int_rd(p.y[s]), iz = __float2int_rd(p.z[s]);
         const bool inb = (unsigned)ix < (unsigned)e.nx && (unsigned)iy < (unsigned)e.ny && (unsigned)iz < (unsigned)e.nz;
         const uint32_t brick = (uint32_t)(ix >> 3) + (uint32_t)e.nbx * ((uint32_t)(iy >> 3) + (uint32_t)e.nby * (uint32_t)(iz >> 3));
         v.mask[s] = inb ? (1u << (((iy & 3) << 3) | (ix & 7))) : 0u;
-        v.word[s] = inb ? __ldg(e.bricks + (size_t)brick * 16 + ((iz & 7) * 2 + ((iy & 7) >> 2))) : 0u;
+        v.word[s] = inb ? ldg_u32_hint(e.bricks + (size_t)brick * 16 + ((iz & 7) * 2 + ((iy & 7) >> 2)), keep_policy) : 0u;
     }
 }
 

@@ -139,6 +139,7 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
     int head = 0;
     uint32_t phase = 0;
     const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     auto next_slot = [](int st) { return st + 1 == kStages ? 0 : st + 1; };
 
     const int ntiles = (P + T - 1) / T;
@@ -165,12 +166,12 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
                 const uint32_t dst = ring_u32 + (uint32_t)st * (W * 16u), bar = bars_u32 + (uint32_t)st * 8u;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)W * 16u) : "memory");
                 if (cpc > 0)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                                 "l"(pop + (size_t)first * W), "r"((uint32_t)cpc * 16u), "r"(bar) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                                 "l"(pop + (size_t)first * W), "r"((uint32_t)cpc * 16u), "r"(bar), "l"(pol_stream) : "memory");
                 if (cpc < W)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                                      dst + (uint32_t)cpc * 16u),
-                                 "l"(pop + (size_t)second * W + cpc), "r"((uint32_t)(W - cpc) * 16u), "r"(bar) : "memory");
+                                 "l"(pop + (size_t)second * W + cpc), "r"((uint32_t)(W - cpc) * 16u), "r"(bar), "l"(pol_stream) : "memory");
             }
         };
 
@@ -203,7 +204,7 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
                     p.x[s] = v.x; p.y[s] = v.y; p.z[s] = v.z;
                 }
                 VoxRegs<NW> vr;
-                voxel_prefetch<NW>(e, p, vr);
+                voxel_prefetch<NW>(e, p, vr, pol_keep);
 #pragma unroll
                 for (int s = 0; s < NW; ++s) { vword[s] = vr.word[s]; vmask[s] = vr.mask[s]; }
             }
@@ -233,7 +234,7 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
                 const float4 q = row[k > 0 ? k - 1 : 0];
                 cur.x[s] = v.x; cur.y[s] = v.y; cur.z[s] = v.z;
                 prev.x[s] = q.x; prev.y[s] = q.y; prev.z[s] = q.z;
-                if constexpr (GA) stg_stream(dst + k, v);
+                if constexpr (GA) stg_stream_hint(dst + k, v, pol_stream);
             }
             PointAcc<NW, SEM> acc;
             acc.reset();
