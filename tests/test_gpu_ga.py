@@ -273,3 +273,24 @@ def test_select_set_is_the_topk_set_in_index_order(tf, P, k):
     for worst in (False, True):
         got = sel(fit, worst=worst).cpu().numpy()
         assert np.array_equal(got, O.select_set(vals, k, worst=worst))
+
+
+def test_evolve_batch_resume_is_bit_identical(tf, tmp_path):
+    """Checkpoint / resume: Philox is counter-based, so 12 generations == 5 + resume + 7."""
+    torch, L, B = tf
+    rng = np.random.default_rng(0)
+    table = random_table(rng, 40, 64, sem_pf=True)
+    env = B.Environment(L.SEM_PF, table, 0.0)
+    pop = B.init_walks(2, 3000, 32, start=(32, 32, 32), lo=(0, 0, 0), hi=(63, 63, 63))
+    ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, mutation_rate=0.3)
+    full = B.evolve_batch(pop, env, 12, ga, seed=9, history=True)
+    part = B.evolve_batch(pop, env, 5, ga, seed=9)
+    state = B.checkpoint(part, str(tmp_path / "ckpt.pt"))
+    rest = B.evolve_batch(None, env, 7, ga, resume=torch.load(str(tmp_path / "ckpt.pt")))
+    assert rest["generation"] == 12 and state["generation"] == 5
+    assert torch.equal(full["pop"], rest["pop"]) and torch.equal(full["fit"], rest["fit"])
+    assert torch.equal(full["best_path"], rest["best_path"]) and torch.equal(full["best_fit"], rest["best_fit"])
+    assert full["best_history"].shape == (12,) and bool((full["best_history"][1:] >= full["best_history"][:-1]).all())
+    # emergency stop hook (HR:110-112)
+    calls = []
+    assert B.evolve_batch(pop, env, 50, ga, should_stop=lambda: len(calls) >= 3 or calls.append(1)) is None

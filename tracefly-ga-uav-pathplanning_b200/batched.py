@@ -439,24 +439,39 @@ class BestTracker:
 
 
 def evolve_batch(pop, env, generations, ga=None, params=None, seed=0, tapes=None, fused=True, start_generation=0,
-                 should_stop=None, record_best=True, inplace=False):
+                 should_stop=None, record_best=True, inplace=False, history=False, resume=None):
     """Runs `generations` GA generations on the device (HR:109-128 generalised):
     rank -> (select, crossover, mutate) -> fitness, with HR's best tracking.
-    tapes: optional int32[G, npairs, 8] host draws (np.random order, HR:118-120); else Philox.
-    Returns dict(pop, fit, best_path [W,4], best_fit, best_gen)."""
+
+    tapes        optional int32[G, npairs, 8] host draws (np.random order, HR:118-120); else Philox.
+    should_stop  callable polled before every generation (the emergency flag of HR:110-112) -> returns None.
+    history      True -> per-generation best / mean fitness, accumulated on the device (no host sync).
+    resume       a checkpoint made by `checkpoint()` of a previous call's result: the run continues at the
+                 saved generation counter.  Philox is counter-based (pair, generation, island), so a resumed
+                 run is bit-identical to an uninterrupted one.
+    Returns dict(pop, fit, generation, best_path [W,4], best_fit, best_gen[, best_history, mean_history])."""
     ga = ga or L.default_ga_params()
+    if resume is not None:
+        pop, start_generation, seed = resume["pop"].to("cuda"), int(resume["generation"]), int(resume["seed"])
+        inplace = True
     f64 = pop.dtype == torch.float64
     P, W, _ = pop.shape
     params = params or L.default_params(dist_zero_guard=1 if env.semantics != L.SEM_PF else 0)
     k = max(min(ga.n_elite, P), min(ga.n_top, P) if ga.selection == L.SEL_TRUNCATION else 1, 1)
     topk = TopK(P, k, f64=f64, device=pop.device)
     tracker = BestTracker(W, f64=f64, device=pop.device) if record_best else None
+    if tracker is not None and resume is not None and "best_fit" in resume:
+        tracker.best_fit.copy_(resume["best_fit"])
+        tracker.best_path.copy_(resume["best_path"])
+        tracker.best_gen.copy_(resume["best_gen"])
     fit = (fitness_batch_f64(pop, None, env, params) if f64 else fitness_batch(pop, None, env, params, want_collisions=False))[0]
     cur, nxt = (pop if inplace else pop.clone()), torch.empty_like(pop)  # ping-pong buffers
     nfit = torch.empty_like(fit)
     top = torch.empty(k, dtype=torch.int32, device=pop.device)
     if tapes is not None and isinstance(tapes, np.ndarray):
         tapes = torch.from_numpy(np.ascontiguousarray(tapes, np.int32)).to(pop.device)
+    hist_best = torch.empty(generations, dtype=fit.dtype, device=pop.device) if history else None
+    hist_mean = torch.empty(generations, dtype=fit.dtype, device=pop.device) if history else None
     for g in range(generations):
         if should_stop is not None and should_stop():
             return None
@@ -475,10 +490,25 @@ def evolve_batch(pop, env, generations, ga=None, params=None, seed=0, tapes=None
         fit, nfit = nfit, fit
         if tracker is not None:
             tracker.update(cur, fit, 0, gen_no)
-    out = dict(pop=cur, fit=fit)
+        if history:
+            hist_best[g] = fit.max()
+            hist_mean[g] = fit.mean()
+    out = dict(pop=cur, fit=fit, generation=start_generation + generations, seed=seed)
     if tracker is not None:
         out.update(best_path=tracker.best_path, best_fit=tracker.best_fit, best_gen=tracker.best_gen)
+    if history:
+        out.update(best_history=hist_best, mean_history=hist_mean)
     return out
+
+
+def checkpoint(result, path=None):
+    """Checkpoint of an `evolve_batch` result (population, generation counter, Philox seed, best-so-far).
+    With `path` it is written with torch.save; the dict is returned either way."""
+    keep = ("pop", "generation", "seed", "best_path", "best_fit", "best_gen")
+    state = {k: (v.detach().cpu() if isinstance(v, torch.Tensor) else v) for k, v in result.items() if k in keep}
+    if path is not None:
+        torch.save(state, path)
+    return state
 
 
 # ------------------------------------------------------------------------------------ host round trips
