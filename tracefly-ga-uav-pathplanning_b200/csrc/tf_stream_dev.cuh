@@ -156,22 +156,20 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
         TileSums<NW> sums;
         sums.reset();
 
-        // gather child c's two parent pieces into ring slot st (one elected lane issues the TMA)
+        // gather child c's two parent pieces into ring slot st: the lane that OWNS child c issues the two TMA
+        // copies from its own plan registers (no broadcast of the plan to an elected lane)
         auto issue = [&](int c, int st) {
-            const int first = __shfl_sync(0xffffffffu, mine.first, c);
-            const int second = __shfl_sync(0xffffffffu, mine.second, c);
-            const int meta = __shfl_sync(0xffffffffu, mine.meta, c);
-            if (lane == 0) {
-                const int cpc = min(meta_cp(meta), W);
+            if (lane == c) {
+                const int cpc = min(meta_cp(mine.meta), W);
                 const uint32_t dst = ring_u32 + (uint32_t)st * (W * 16u), bar = bars_u32 + (uint32_t)st * 8u;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)W * 16u) : "memory");
                 if (cpc > 0)
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-                                 "l"(pop + (size_t)first * W), "r"((uint32_t)cpc * 16u), "r"(bar), "l"(pol_stream) : "memory");
+                                 "l"(pop + (size_t)mine.first * W), "r"((uint32_t)cpc * 16u), "r"(bar), "l"(pol_stream) : "memory");
                 if (cpc < W)
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                                      dst + (uint32_t)cpc * 16u),
-                                 "l"(pop + (size_t)second * W + cpc), "r"((uint32_t)(W - cpc) * 16u), "r"(bar), "l"(pol_stream) : "memory");
+                                 "l"(pop + (size_t)mine.second * W + cpc), "r"((uint32_t)(W - cpc) * 16u), "r"(bar), "l"(pol_stream) : "memory");
             }
         };
 
