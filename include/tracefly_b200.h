@@ -291,6 +291,11 @@ int tf_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_byt
 /* Philox4x32-10 block, exposed so host code and tests can reproduce device draws. */
 void tf_philox4x32_10(uint32_t key0, uint32_t key1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                       uint32_t out[4]);
+/* Self-test of the library's FP32 square root (rsqrt seed + fma Newton step, used for segment lengths and
+ * obstacle distances; the FP32 model of HR:51-52 / PF:162 needs it correctly rounded): adds to
+ * *mismatches_dev (u64, device, caller-zeroed) the number of bit patterns in [first_bits, first_bits + count)
+ * whose result differs from sqrt.rn.f32.  count <= 2^32. */
+int tf_selftest_sqrt(uint32_t first_bits, uint64_t count, uint64_t* mismatches_dev, void* stream);
 /* Options.  TF_OPT_DISABLE_STREAM = 1 forces the LSU-path kernels even where the TMA-staged
  * kernels apply (W = 32 / 64, fixed length); both give bit-identical results. */
 #define TF_OPT_DISABLE_STREAM 1

@@ -266,3 +266,14 @@ def test_voxelize_points(tf):
     b = idx[ok, 0] + dims[0] * (idx[ok, 1] + dims[1] * idx[ok, 2])
     np.bitwise_or.at(lin, b >> 5, (np.uint32(1) << (b & 31).astype(np.uint32)))
     assert ok.sum() > 1000 and np.array_equal(got, O.voxel_pack_linear(lin, *dims))
+
+
+def test_library_sqrt_is_correctly_rounded_for_every_float(tf):
+    """The FP32 model needs IEEE sqrt (HR:51-52, PF:162).  The library's own sequence (rsqrt seed + fma
+    Newton step, zero folded in) must equal sqrt.rn.f32 for all 2^32 bit patterns."""
+    torch, L, B = tf
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for first in (0, 1 << 31):
+        L.check(L.lib.tf_selftest_sqrt(first, 1 << 31, bad.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                "tf_selftest_sqrt")
+    assert int(bad.item()) == 0

@@ -656,6 +656,27 @@ extern "C" void tf_philox4x32_10(uint32_t key0, uint32_t key1, uint32_t c0, uint
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
+namespace tf {
+__global__ void selftest_sqrt_kernel(uint32_t lo, uint64_t n, unsigned long long* bad) {
+    unsigned long long mine = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float(lo + (uint32_t)i);
+        const uint32_t a = __float_as_uint(sqrt_rn(x)), b = __float_as_uint(__fsqrt_rn(x));
+        mine += (a != b && !(isnan(__uint_as_float(a)) && isnan(__uint_as_float(b)))) ? 1 : 0;
+    }
+    if (mine) atomicAdd(bad, mine);
+}
+}  // namespace tf
+
+extern "C" int tf_selftest_sqrt(uint32_t first_bits, uint64_t count, uint64_t* mismatches_dev, void* stream) {
+    if (!mismatches_dev || count > (1ull << 32)) return TF_ERR_INVALID;
+    if (count == 0) return TF_OK;
+    tf::selftest_sqrt_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(first_bits, count,
+                                                                      (unsigned long long*)mismatches_dev);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+
 extern "C" int tf_set_option(int option, int value) {
     if (option == TF_OPT_DISABLE_STREAM) { tf::g_disable_stream = value != 0; return TF_OK; }
     return TF_ERR_INVALID;

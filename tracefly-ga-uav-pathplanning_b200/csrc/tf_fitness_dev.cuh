@@ -95,7 +95,7 @@ __device__ __forceinline__ void eval_static_chunk(const EnvDev& e, const Tables&
                 float d2 = dist2(x[s] - o.x, y[s] - o.y, z[s] - o.z);
                 hit |= (d2 <= s2) ? (1u << s) : 0u;
                 if (d2 < bound[s]) {
-                    best[s] = fminf(best[s], fmaxf(0.0f, __fsub_rn(__fsqrt_rn(d2), o.w)));
+                    best[s] = fminf(best[s], fmaxf(0.0f, __fsub_rn(sqrt_rn(d2), o.w)));
                     bound[s] = prune_bound(best[s], smax);
                 }
             }
@@ -111,7 +111,7 @@ __device__ __forceinline__ void eval_static_chunk(const EnvDev& e, const Tables&
                 hit |= in ? (1u << s) : 0u;
                 float d2 = dist2(dx, dy, dz);
                 if (d2 < bound[s]) {
-                    best[s] = fminf(best[s], fmaxf(0.0f, __fsub_rn(__fsqrt_rn(d2), o.w)));
+                    best[s] = fminf(best[s], fmaxf(0.0f, __fsub_rn(sqrt_rn(d2), o.w)));
                     bound[s] = prune_bound(best[s], smax);
                 }
             }
@@ -128,7 +128,7 @@ __device__ __forceinline__ void eval_static_chunk(const EnvDev& e, const Tables&
                 hit |= in ? (1u << s) : 0u;
                 float qx = fmaxf(__fsub_rn(ax, h.x), 0.0f), qy = fmaxf(__fsub_rn(ay, h.y), 0.0f),
                       qz = fmaxf(__fsub_rn(az, h.z), 0.0f);
-                best[s] = fminf(best[s], __fsqrt_rn(dist2(qx, qy, qz)));
+                best[s] = fminf(best[s], sqrt_rn(dist2(qx, qy, qz)));
             }
         }
     }
@@ -148,10 +148,10 @@ __device__ __forceinline__ void static_test(const EnvDev& e, int id, float x, fl
         if (id < s_end) {
             const float d2 = dist2(dx, dy, dz);
             hit = hit || (d2 <= __fmul_rn(o.w, o.w));
-            best = fminf(best, fmaxf(0.0f, __fsub_rn(__fsqrt_rn(d2), o.w)));
+            best = fminf(best, fmaxf(0.0f, __fsub_rn(sqrt_rn(d2), o.w)));
         } else if (id < c_end) {
             hit = hit || (fabsf(dx) <= o.w && fabsf(dy) <= o.w && fabsf(dz) <= o.w);
-            best = fminf(best, fmaxf(0.0f, __fsub_rn(__fsqrt_rn(dist2(dx, dy, dz)), o.w)));
+            best = fminf(best, fmaxf(0.0f, __fsub_rn(sqrt_rn(dist2(dx, dy, dz)), o.w)));
         } else if (id < y_end) {
             const float h = __fmul_rn(2.0f, o.w), az = fabsf(dz);
             hit = hit || (fabsf(dx) <= o.w && fabsf(dy) <= o.w && az <= h);
@@ -162,7 +162,7 @@ __device__ __forceinline__ void static_test(const EnvDev& e, int id, float x, fl
             hit = hit || (ax <= h.x && ay <= h.y && az <= h.z);
             const float qx = fmaxf(__fsub_rn(ax, h.x), 0.0f), qy = fmaxf(__fsub_rn(ay, h.y), 0.0f),
                         qz = fmaxf(__fsub_rn(az, h.z), 0.0f);
-            best = fminf(best, __fsqrt_rn(dist2(qx, qy, qz)));
+            best = fminf(best, sqrt_rn(dist2(qx, qy, qz)));
         }
     }
 }
@@ -341,12 +341,12 @@ __device__ __forceinline__ void eval_point_full(const EnvDev& e, const Tables& t
     uint32_t hit = 0;
     float best[1] = {INFINITY};
     eval_static<SEM, 1>(e, t, xs, ys, zs, hit, best);
-    float dn = (SEM == TF_SEM_HR) ? __fsqrt_rn(best[0]) : best[0];
+    float dn = (SEM == TF_SEM_HR) ? sqrt_rn(best[0]) : best[0];
     if constexpr (XF >= 1) {
         if (e.n_dyn > 0) {
             float m2[1] = {INFINITY};
             eval_dynamic<1>(e, t, xs, ys, zs, tms, hit, m2);
-            dn = fminf(dn, __fsqrt_rn(m2[0]));
+            dn = fminf(dn, sqrt_rn(m2[0]));
         }
     }
     if constexpr (VOX) hit |= voxel_hit(e, x, y, z) ? 1u : 0u;
@@ -449,7 +449,7 @@ __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_para
     const bool has_dist = (SEM != TF_SEM_NONE) || (XF >= 1 && e.n_dyn > 0);
     float dn[NW];
 #pragma unroll
-    for (int s = 0; s < NW; ++s) dn[s] = (SEM == TF_SEM_HR) ? __fsqrt_rn(acc.best[s]) : acc.best[s];
+    for (int s = 0; s < NW; ++s) dn[s] = (SEM == TF_SEM_HR) ? sqrt_rn(acc.best[s]) : acc.best[s];
     if constexpr (XF >= 1) {
         if (e.n_dyn > 0) {
             float m2[NW], tm[NW];
@@ -460,7 +460,7 @@ __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_para
             }
             eval_dynamic<NW>(e, t, cur.x, cur.y, cur.z, tm, hit, m2);
 #pragma unroll
-            for (int s = 0; s < NW; ++s) dn[s] = fminf(dn[s], __fsqrt_rn(m2[s]));
+            for (int s = 0; s < NW; ++s) dn[s] = fminf(dn[s], sqrt_rn(m2[s]));
         }
     }
     const int S = (XF >= 2) ? max(prm.samples_per_segment, 1) : 1;
@@ -488,7 +488,7 @@ __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_para
         }
         if (valid && k >= 1) {
             float dx = cur.x[s] - px, dy = cur.y[s] - py, dz = cur.z[s] - pz;
-            a_dist = __fadd_rn(a_dist, __fsqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
+            a_dist = __fadd_rn(a_dist, sqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
             a_alt = __fadd_rn(a_alt, fabsf(dz));                         // HR:44
             if (k <= L - 2) turns += (cur.x[s] != px || cur.y[s] != py) ? 1 : 0;  // HR:38-40,43
             if constexpr (XF >= 2) {

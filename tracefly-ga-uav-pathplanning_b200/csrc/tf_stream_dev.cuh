@@ -33,7 +33,7 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
     const bool has_dist = (SEM != TF_SEM_NONE) || (XF >= 1 && e.n_dyn > 0);
     float dn[NW];
 #pragma unroll
-    for (int s = 0; s < NW; ++s) dn[s] = (SEM == TF_SEM_HR) ? __fsqrt_rn(acc.best[s]) : acc.best[s];
+    for (int s = 0; s < NW; ++s) dn[s] = (SEM == TF_SEM_HR) ? sqrt_rn(acc.best[s]) : acc.best[s];
     if constexpr (XF >= 1) {
         if (e.n_dyn > 0) {
             float m2[NW], tm[NW];
@@ -44,7 +44,7 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
             }
             eval_dynamic<NW>(e, t, cur.x, cur.y, cur.z, tm, hit, m2);
 #pragma unroll
-            for (int s = 0; s < NW; ++s) dn[s] = fminf(dn[s], __fsqrt_rn(m2[s]));
+            for (int s = 0; s < NW; ++s) dn[s] = fminf(dn[s], sqrt_rn(m2[s]));
         }
     }
     const int S = (XF >= 2) ? max(prm.samples_per_segment, 1) : 1;
@@ -63,7 +63,7 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
         if (s > 0 || lane > 0) {  // k >= 1
             const float px = prev.x[s], py = prev.y[s], pz = prev.z[s];
             const float dx = cur.x[s] - px, dy = cur.y[s] - py, dz = cur.z[s] - pz;
-            a_dist = __fadd_rn(a_dist, __fsqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
+            a_dist = __fadd_rn(a_dist, sqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
             a_alt = __fadd_rn(a_alt, fabsf(dz));                         // HR:44
             if (k <= W - 2) turns += (cur.x[s] != px || cur.y[s] != py) ? 1 : 0;  // HR:38-40,43
             if constexpr (XF >= 2) {
@@ -179,20 +179,17 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
             mbar_wait(&bars[st], (phase >> st) & 1u);
             phase ^= 1u << st;
             if constexpr (GA) {
-                const int mp = meta_mp(__shfl_sync(0xffffffffu, mine.meta, c));
-                if (mp >= 0) {  // warp-uniform; HR:97-98
-                    const float dx = __shfl_sync(0xffffffffu, mine.dx, c);
-                    const float dy = __shfl_sync(0xffffffffu, mine.dy, c);
-                    const float dz = __shfl_sync(0xffffffffu, mine.dz, c);
-                    if (lane == (mp & 31)) {
+                if (lane == c) {  // the owning lane applies its child's mutation (HR:97-98)
+                    const int mp = meta_mp(mine.meta);
+                    if (mp >= 0) {
                         float4 v = row[mp];
-                        v.x = __fadd_rn(v.x, dx);
-                        v.y = __fadd_rn(v.y, dy);
-                        v.z = __fadd_rn(v.z, dz);
+                        v.x = __fadd_rn(v.x, mine.dx);
+                        v.y = __fadd_rn(v.y, mine.dy);
+                        v.z = __fadd_rn(v.z, mine.dz);
                         row[mp] = v;
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
             }
             if constexpr (VOX) {
                 Lanes<NW> p;
