@@ -193,12 +193,13 @@ def test_init_populations(tf):
     assert np.array_equal(exp, got.cpu().numpy())
 
 
+@pytest.mark.parametrize("P", [5003, 230003, 700001])   # tiles of 4 / of 32 (static) / dynamic tickets; ragged
 @pytest.mark.parametrize("W", [32, 64])
 @pytest.mark.parametrize("env_kind", ["none", "pf", "vox+dyn+haz"])
-def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind):
-    """The TMA-staged kernels (W = 32/64/128) must give bit-identical results to the LSU-path kernels."""
+def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind, P):
+    """The TMA-staged kernels (W = 32/64), in both schedules (two chromosomes per warp step / one), must give
+    bit-identical results to the LSU-path kernels."""
     torch, L, B = tf
-    P = 5003
     rng = np.random.default_rng(W)
     dims = (64, 64, 64)
     table = random_table(rng, 150, 64, sem_pf=True)
@@ -217,19 +218,22 @@ def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind):
     prm = L.default_params(hazard_weight=0.3)
     pop = B.init_walks(5, P, W, start=(32, 32, 32), lo=(0, 0, 0), hi=(63, 63, 63))
     ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=3, mutation_rate=0.5, n_elite=3)
-    res = {}
-    for disable in (0, 1):
+    res = []
+    for disable, schedule in ((0, 0), (0, 1), (1, 0)):
         L.set_option(L.OPT_DISABLE_STREAM, disable)
+        L.set_option(L.OPT_STREAM_SCHEDULE, schedule)
         try:
             fit, coll = B.fitness_batch(pop, None, env, prm)
             top = B.rank_topk(fit, 3)
             out = B.generation(env, pop, fit, top, ga, prm, seed=77, generation=9, want_collisions=True, want_parity=True)
             torch.cuda.synchronize()
-            res[disable] = (fit, coll) + out
+            res.append((fit, coll) + out)
         finally:
             L.set_option(L.OPT_DISABLE_STREAM, 0)
-    for a, b in zip(res[0], res[1]):
-        assert torch.equal(a, b)
+            L.set_option(L.OPT_STREAM_SCHEDULE, 0)
+    for other in res[1:]:
+        for a, b in zip(res[0], other):
+            assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("fmt", ["f32", "i16"])

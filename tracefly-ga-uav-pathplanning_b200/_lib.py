@@ -138,6 +138,7 @@ def philox(key0, key1, c0, c1, c2, c3):
 
 
 OPT_DISABLE_STREAM = 1
+OPT_STREAM_SCHEDULE = 2
 
 
 def set_option(option, value):
@@ -146,3 +147,7 @@ def set_option(option, value):
 
 def launch_count():
     return int(lib.tf_launch_count())
+
+
+if os.environ.get("TRACEFLY_STREAM_SCHEDULE"):      # A/B knob for measurements (see TF_OPT_STREAM_SCHEDULE)
+    set_option(OPT_STREAM_SCHEDULE, int(os.environ["TRACEFLY_STREAM_SCHEDULE"]))

@@ -6,6 +6,8 @@
 
 #include <vector>
 
+#include <mutex>
+
 #include "tf_common.cuh"
 
 namespace tf {
@@ -13,6 +15,7 @@ namespace tf {
 thread_local int g_last_cuda_error = 0;
 long long g_launch_count = 0;
 int g_disable_stream = 0;
+int g_stream_schedule = 0;
 static int g_sm_count = 0;
 static int g_dev_checked = 0;
 
@@ -30,6 +33,26 @@ int ensure_device() {
     return TF_OK;
 }
 int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+
+int* sched_slot() {
+    constexpr int kSlots = 4096, kMaxDev = 64;
+    static int* rings[kMaxDev] = {nullptr};
+    static unsigned next[kMaxDev] = {0};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+    if (rings[dev] == nullptr) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (rings[dev] == nullptr) {
+            int* p = nullptr;
+            if (cudaMalloc(&p, (size_t)kSlots * 2 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            if (cudaMemset(p, 0, (size_t)kSlots * 2 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return nullptr; }
+            rings[dev] = p;
+        }
+    }
+    const unsigned i = __atomic_fetch_add(&next[dev], 1u, __ATOMIC_RELAXED) % kSlots;
+    return rings[dev] + 2 * i;
+}
 
 // ------------------------------------------------------------------ voxel kernels
 __device__ __forceinline__ size_t brick_word(int x, int y, int z, int nbx, int nby) {
@@ -679,6 +702,7 @@ extern "C" int tf_selftest_sqrt(uint32_t first_bits, uint64_t count, uint64_t* m
 
 extern "C" int tf_set_option(int option, int value) {
     if (option == TF_OPT_DISABLE_STREAM) { tf::g_disable_stream = value != 0; return TF_OK; }
+    if (option == TF_OPT_STREAM_SCHEDULE && (value == 0 || value == 1)) { tf::g_stream_schedule = value; return TF_OK; }
     return TF_ERR_INVALID;
 }
 

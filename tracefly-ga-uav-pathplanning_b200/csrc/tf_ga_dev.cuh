@@ -76,19 +76,30 @@ __device__ __forceinline__ ChildPlan<NW> plan_child(int slot, int ne, const F* _
         } else {  // tournament: k uniform entrants per parent, winner under the stable order
             ia = ib = -1;
             F fa = (F)0, fb = (F)0;
-            for (int e2 = 0; e2 < ga.tournament_k; e2 += 2) {
-                const U4 q = philox4x32_10(k0, k1, (uint32_t)j, gen, ga.stream_id, CALL_TOURN + (uint32_t)(e2 >> 1));
-                int ea = (int)mulhi32(q.x, (uint32_t)P), eb = (int)mulhi32(q.y, (uint32_t)P);
-                F fea = fit[ea], feb = fit[eb];
-                if (ia < 0 || better(fea, ea, fa, ia)) { ia = ea; fa = fea; }
-                if (ib < 0 || better(feb, eb, fb, ib)) { ib = eb; fb = feb; }
-                if (e2 + 1 < ga.tournament_k) {
-                    ea = (int)mulhi32(q.z, (uint32_t)P);
-                    eb = (int)mulhi32(q.w, (uint32_t)P);
-                    fea = fit[ea];
-                    feb = fit[eb];
-                    if (better(fea, ea, fa, ia)) { ia = ea; fa = fea; }
-                    if (better(feb, eb, fb, ib)) { ib = eb; fb = feb; }
+            // entrants e = 0, 1, ... of parent a are q.x, q.z of Philox call CALL_TOURN + (e >> 1), parent b's are
+            // q.y, q.w.  Four entrants per parent at a time: all draws, then all 8 fitness gathers, then the
+            // comparisons in entrant order, so a batch costs one memory round trip instead of two.
+            for (int e4 = 0; e4 < ga.tournament_k; e4 += 4) {
+                const int n = min(4, ga.tournament_k - e4);
+                const U4 q0 = philox4x32_10(k0, k1, (uint32_t)j, gen, ga.stream_id, CALL_TOURN + (uint32_t)(e4 >> 1));
+                U4 q1 = U4{0, 0, 0, 0};
+                if (n > 2) q1 = philox4x32_10(k0, k1, (uint32_t)j, gen, ga.stream_id, CALL_TOURN + (uint32_t)(e4 >> 1) + 1u);
+                const int ea[4] = {(int)mulhi32(q0.x, (uint32_t)P), (int)mulhi32(q0.z, (uint32_t)P),
+                                   (int)mulhi32(q1.x, (uint32_t)P), (int)mulhi32(q1.z, (uint32_t)P)};
+                const int eb[4] = {(int)mulhi32(q0.y, (uint32_t)P), (int)mulhi32(q0.w, (uint32_t)P),
+                                   (int)mulhi32(q1.y, (uint32_t)P), (int)mulhi32(q1.w, (uint32_t)P)};
+                F fea[4], feb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {  // indices of unused entrants are 0: a harmless gather
+                    fea[i] = fit[ea[i]];
+                    feb[i] = fit[eb[i]];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (i < n) {
+                        if (ia < 0 || better(fea[i], ea[i], fa, ia)) { ia = ea[i]; fa = fea[i]; }
+                        if (ib < 0 || better(feb[i], eb[i], fb, ib)) { ib = eb[i]; fb = feb[i]; }
+                    }
                 }
             }
         }

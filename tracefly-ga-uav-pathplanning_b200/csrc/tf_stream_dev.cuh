@@ -254,17 +254,293 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 }
 
 
+// ---------------------------------------------------------------------------------------------------
+// "duo" schedule of the same kernel: a warp evaluates TWO chromosomes at a time, one per half-warp.
+// Lane h = lane & 15 of a half owns waypoints h, h+16, h+32, ... of its half's chromosome (W/16 per lane).
+// Why: with one chromosome per warp-iteration the per-chromosome overhead (mbarrier wait, TMA issue, five
+// butterfly stages per total, loop bookkeeping) is about half of the 330 warp-instructions a chromosome
+// costs, and the kernel is issue-bound (ncu round 1: issue-active 78 %).  Two chromosomes per iteration
+// share the wait / loop / reduction instructions, and the butterfly needs only stages 8, 4, 2, 1 across
+// lanes: stage 16 is a register add, because lane h holds the partial of "virtual lane" h (even m) and of
+// virtual lane h + 16 (odd m) of the FP32 model (oracle: lane l owns waypoints l, l+32, ...; tree32).
+// Every floating-point add has the same two operands as in the one-chromosome schedule, so the results
+// are bit-identical (tests run both through TF_OPT_STREAM_SCHEDULE).
+// Tile bookkeeping: lanes 0-15 own children [0, T/2) of the tile, lanes 16-31 own [T/2, T); pair j =
+// children j and T/2 + j = lanes j and 16 + j, so every total ends in the half where its owner sits.
+template <int NW, int SEM, bool VOX, int XF, bool GA>
+__global__ void __launch_bounds__(kBlockThreads, (XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? 3 : 0))
+duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
+           const __grid_constant__ tf_ga_params ga, const float4* __restrict__ pop,
+           const float* __restrict__ fit, const int32_t* __restrict__ top_idx,
+           const tf_draw* __restrict__ tape, uint64_t seed, uint32_t gen, int P, int T,
+           float4* __restrict__ next, float* __restrict__ out_fit, uint32_t* __restrict__ out_coll,
+           int32_t* __restrict__ sel, int32_t* __restrict__ cpo, int n_big, int n_tickets, int* __restrict__ sched) {
+    constexpr int W = 32 * NW, NL = 2 * NW, kPairStages = kStages / 2;
+    extern __shared__ __align__(128) unsigned char smem_stream[];
+    unsigned char* smem = smem_stream;
+    const SmemLayout sm = carve_smem(e, smem);
+    const Tables tabs{sm.A, sm.B, sm.dA, sm.dB};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, h = lane & 15, half = lane >> 4;
+    const size_t tables = (smem_bytes_for(e) + 127) & ~(size_t)127;
+    float4* ring = reinterpret_cast<float4*>(smem + tables) + (size_t)warp * kStages * W;   // kPairStages x 2 rows
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tables + (size_t)kWarpsPerBlock * kStages * W * 16) + warp * kStages;
+    const int ne = GA ? min(ga.n_elite, P) : 0;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kPairStages; ++i) mbar_init(&bars[i], 2);   // one arrival per half
+    }
+    if ((SEM != TF_SEM_NONE && e.n_smem > 0) || (XF >= 1 && e.n_dyn_smem > 0)) {
+        if (threadIdx.x == 0) mbar_init(sm.bar, 1);
+        fence_mbar_init();
+        __syncthreads();
+        if (threadIdx.x == 0)
+            stage_chunk(e, sm.A, sm.B, 0, min(e.n_smem, kTableCap), sm.bar, XF >= 1 && e.n_dyn_smem > 0, sm.dA, sm.dB);
+        mbar_wait(sm.bar, 0);
+    } else {
+        fence_mbar_init();
+        __syncwarp();
+    }
+
+    int head = 0;
+    uint32_t phase = 0;
+    const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    auto next_stage = [](int st) { return st + 1 == kPairStages ? 0 : st + 1; };
+    const bool has_dist = (SEM != TF_SEM_NONE) || (XF >= 1 && e.n_dyn > 0);
+
+    // Dynamic schedule: the grid is persistent (one CTA per resident slot) and every warp draws tile tickets
+    // from a global counter.  Tickets [0, n_big) are tiles of T children, the rest are tiles of T/2 that
+    // cover the end of the population, so all warps run dry within half a tile of each other (ncu round 1,
+    // static schedule: SMs active 92 % of the kernel, 28.7 of 32 warp slots filled while active).  The next
+    // ticket is drawn at the top of a tile, so the atomic's latency hides behind the tile's work.
+    // Short runs (sched == nullptr) keep the static assignment: ticket = global warp index, then stride.
+    const bool dynamic = sched != nullptr;
+    auto draw = [&]() {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(sched, 1);
+        return t;
+    };
+    int ticket = dynamic ? __shfl_sync(0xffffffffu, draw(), 0) : (int)(blockIdx.x * kWarpsPerBlock) + warp;
+    while (ticket < n_tickets) {
+        const int ahead = dynamic ? draw() : ticket + (int)(gridDim.x * kWarpsPerBlock);
+        const int Tt = ticket < n_big ? T : (T >> 1), hT = Tt >> 1;
+        const int slot0 = ticket < n_big ? ticket * T : n_big * T + (ticket - n_big) * Tt;
+        const int cnt = min(Tt, P - slot0);
+        // ---- phase A (lane = child of the tile)
+        const int myc = half * hT + h;
+        const bool own = h < hT && myc < cnt;
+        ChildPlan<NW> mine;
+        if constexpr (GA) {
+            mine = plan_slot<NW, float>(own ? slot0 + myc : P, ne, fit, nullptr, top_idx, tape, seed, gen, ga, P, W, sel, cpo);
+        } else {
+            mine = plan_elite<NW>(min(slot0 + myc, P - 1), W);
+        }
+        TileSums<NW> sums;
+        sums.reset();
+
+        // pair j -> stage st: each owning lane gathers its own child's two parent pieces (or just arrives
+        // when the pair has no second child)
+        auto issue = [&](int j, int st) {
+            if (h == j) {
+                const uint32_t bar = bars_u32 + (uint32_t)st * 8u;
+                if (own) {
+                    const int cpc = min(meta_cp(mine.meta), W);
+                    const uint32_t dst = ring_u32 + (uint32_t)(st * 2 + half) * (W * 16u);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)W * 16u) : "memory");
+                    if (cpc > 0)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                                     "l"(pop + (size_t)mine.first * W), "r"((uint32_t)cpc * 16u), "r"(bar), "l"(pol_stream) : "memory");
+                    if (cpc < W)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                                         dst + (uint32_t)cpc * 16u),
+                                     "l"(pop + (size_t)mine.second * W + cpc), "r"((uint32_t)(W - cpc) * 16u), "r"(bar), "l"(pol_stream) : "memory");
+                } else {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+                }
+            }
+        };
+
+        const int npairs = min(cnt, hT);
+        {
+            int st = head;
+            for (int j = 0; j < min(npairs, kPairStages); ++j) { issue(j, st); st = next_stage(st); }
+        }
+#pragma unroll 1
+        for (int j = 0; j < npairs; ++j) {
+            const bool hasB = hT + j < cnt;                       // warp-uniform
+            const bool live = half == 0 || hasB;                  // this half has a chromosome of its own
+            float4* row = ring + (head * 2 + (hasB ? half : 0)) * W;
+            mbar_wait(&bars[head], (phase >> head) & 1u);
+            phase ^= 1u << head;
+            if constexpr (GA) {
+                if (h == j && own) {  // the owning lane applies its child's mutation (HR:97-98)
+                    const int mp = meta_mp(mine.meta);
+                    if (mp >= 0) {
+                        float4 v = row[mp];
+                        v.x = __fadd_rn(v.x, mine.dx);
+                        v.y = __fadd_rn(v.y, mine.dy);
+                        v.z = __fadd_rn(v.z, mine.dz);
+                        row[mp] = v;
+                    }
+                }
+                __syncwarp();
+            }
+            Lanes<NL> cur, prev;
+            float4* dst = GA ? next + (size_t)(slot0 + half * hT + j) * W : nullptr;
+#pragma unroll
+            for (int m = 0; m < NL; ++m) {
+                const int k = h + 16 * m;
+                const float4 v = row[k];
+                const float4 q = row[k > 0 ? k - 1 : 0];
+                cur.x[m] = v.x; cur.y[m] = v.y; cur.z[m] = v.z;
+                prev.x[m] = q.x; prev.y[m] = q.y; prev.z[m] = q.z;
+                if constexpr (GA) {
+                    if (live) stg_stream_hint(dst + k, v, pol_stream);
+                }
+            }
+            VoxRegs<NL> vr;
+            if constexpr (VOX) voxel_prefetch<NL>(e, cur, vr, pol_keep);
+            PointAcc<NL, SEM> acc;
+            acc.reset();
+            if constexpr (SEM != TF_SEM_NONE) eval_static<SEM, NL>(e, tabs, cur.x, cur.y, cur.z, acc.hit, acc.best);
+            uint32_t hit = acc.hit;
+            float dn[NL];
+#pragma unroll
+            for (int m = 0; m < NL; ++m) dn[m] = (SEM == TF_SEM_HR) ? sqrt_rn(acc.best[m]) : acc.best[m];
+            if constexpr (XF >= 1) {
+                if (e.n_dyn > 0) {
+                    float m2[NL], tm[NL];
+#pragma unroll
+                    for (int m = 0; m < NL; ++m) {
+                        m2[m] = INFINITY;
+                        tm[m] = (float)(h + 16 * m);
+                    }
+                    eval_dynamic<NL>(e, tabs, cur.x, cur.y, cur.z, tm, hit, m2);
+#pragma unroll
+                    for (int m = 0; m < NL; ++m) dn[m] = fminf(dn[m], sqrt_rn(m2[m]));
+                }
+            }
+            // per-lane partials of virtual lanes h (even m) and h + 16 (odd m), accumulated in waypoint order
+            float a_prox[2] = {0.0f, 0.0f}, a_dist[2] = {0.0f, 0.0f}, a_alt[2] = {0.0f, 0.0f}, a_haz[2] = {0.0f, 0.0f};
+            int turns = 0, ncoll = 0;
+            uint32_t cwords[NL];
+#pragma unroll
+            for (int m = 0; m < NL; ++m) {
+                const int k = h + 16 * m, v = m & 1;
+                if (has_dist) a_prox[v] = __fadd_rn(a_prox[v], __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[m])));  // HR:46
+                if constexpr (XF >= 1) {
+                    if (e.hazard != nullptr) a_haz[v] = __fadd_rn(a_haz[v], hazard_sample(e, cur.x[m], cur.y[m], (float)k));
+                }
+                if (m > 0 || h > 0) {  // k >= 1
+                    const float px = prev.x[m], py = prev.y[m], pz = prev.z[m];
+                    const float dx = cur.x[m] - px, dy = cur.y[m] - py, dz = cur.z[m] - pz;
+                    a_dist[v] = __fadd_rn(a_dist[v], sqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
+                    a_alt[v] = __fadd_rn(a_alt[v], fabsf(dz));                      // HR:44
+                    if (m < NL - 1 || h < 15) turns += (cur.x[m] != px || cur.y[m] != py) ? 1 : 0;  // k <= W-2, HR:38-40,43
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < NL; ++m) {
+                bool hm = (hit >> m) & 1u;
+                if constexpr (VOX) hm = hm || (vr.word[m] & vr.mask[m]) != 0u;
+                cwords[m] = __ballot_sync(0xffffffffu, hm);
+                ncoll += hm ? 1 : 0;
+            }
+            // totals: stage 16 of the butterfly is the add of the two virtual lanes, stages 8..1 stay in the half
+            auto half_sum = [](const float (&a)[2]) {
+                float r = __fadd_rn(a[0], a[1]);
+#pragma unroll
+                for (int x = 8; x >= 1; x >>= 1) r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, x));
+                return r;
+            };
+            const float dist = half_sum(a_dist), alt = half_sum(a_alt);
+            const uint32_t both = __reduce_add_sync(0xffffffffu, (uint32_t)(turns | (ncoll << 7)) << (half * 16));
+            if (h == j) {
+                const uint32_t t14 = (both >> (half * 16)) & 0xffffu;
+                sums.dist = dist; sums.alt = alt;
+                sums.packed = (int)((t14 & 127u) | ((t14 >> 7) << 10));
+#pragma unroll
+                for (int w = 0; w < NW; ++w)
+                    sums.cw[w] = __byte_perm(cwords[2 * w], cwords[2 * w + 1], half ? 0x7632 : 0x5410);
+            }
+            if (has_dist) {
+                const float prox = half_sum(a_prox);
+                if (h == j) sums.prox = prox;
+            }
+            if constexpr (XF >= 1) {
+                if (e.hazard != nullptr) {
+                    const float haz = half_sum(a_haz);
+                    if (h == j) sums.haz = haz;
+                }
+            }
+            __syncwarp();  // every lane is done with this stage: refill it
+            if (j + kPairStages < npairs) issue(j + kPairStages, head);
+            head = next_stage(head);
+        }
+        // ---- phase C (lane = child of the tile)
+        if (own) {
+            const int slot = slot0 + myc;
+            out_fit[slot] = combine_fitness<NW, XF>(e, prm, sums);
+            if (out_coll) {
+#pragma unroll
+                for (int s = 0; s < NW; ++s) out_coll[(size_t)slot * NW + s] = sums.cw[s];
+            }
+        }
+        ticket = dynamic ? __shfl_sync(0xffffffffu, ahead, 0) : ahead;
+    }
+    // the last warp of the grid to run dry hands the counters back zeroed for the next launch
+    if (dynamic && lane == 0) {
+        if (atomicAdd(sched + 1, 1) == (int)(gridDim.x * kWarpsPerBlock) - 1) {
+            sched[0] = 0;
+            sched[1] = 0;
+        }
+    }
+}
+
 template <int NW, int SEM, bool VOX, int XF, bool GA>
 static int launch_stream(const StreamArgs& a) {
-    auto kern = stream_kernel<NW, SEM, VOX, XF, GA>;
     const size_t smem = stream_smem_bytes(*a.e, a.W);
-    if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int T = tile_size_for(a.P);
-    const int ntiles = (a.P + T - 1) / T;
-    const int grid = min((ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
+    if (g_stream_schedule == 1) {  // one chromosome per warp step, static tile assignment
+        auto kern = stream_kernel<NW, SEM, VOX, XF, GA>;
+        if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int ntiles = (a.P + T - 1) / T;
+        const int grid = min((ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
+        kern<<<grid, kBlockThreads, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
+                                                  a.top_idx, a.tape, a.seed, a.gen, a.P, T,
+                                                  reinterpret_cast<float4*>(a.next), a.out_fit, a.out_coll, a.sel, a.cpo);
+        TF_LAUNCH_CHECK();
+        return TF_OK;
+    }
+    auto kern = duo_kernel<NW, SEM, VOX, XF, GA>;
+    if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t occ_smem = ~(size_t)0;  // resident CTAs per SM of this variant with this much shared memory
+    static int occ_cached = 0;
+    int occ = occ_cached;
+    if (occ_smem != smem || occ <= 0) {
+        TF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlockThreads, smem));
+        occ_cached = occ;
+        occ_smem = smem;
+    }
+    const int resident_warps = sm_count() * max(occ, 1) * kWarpsPerBlock;
+    // long runs (>= 4 tiles per resident warp): persistent grid, tickets from a global counter, and the
+    // population ends in half-size tiles, two per resident warp; short runs: static assignment
+    int n_big = (a.P + T - 1) / T, n_small = 0;
+    int* sched = nullptr;
+    int grid = min((n_big + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
+    if (T >= 8 && a.P / T >= 4 * resident_warps) {
+        const int Ts = T >> 1;
+        n_big = (a.P - 2 * resident_warps * Ts) / T;
+        n_small = (a.P - n_big * T + Ts - 1) / Ts;
+        sched = sched_slot();
+        if (sched == nullptr) return TF_ERR_NOMEM;
+        grid = sm_count() * max(occ, 1);
+    }
     kern<<<grid, kBlockThreads, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
                                               a.top_idx, a.tape, a.seed, a.gen, a.P, T,
-                                              reinterpret_cast<float4*>(a.next), a.out_fit, a.out_coll, a.sel, a.cpo);
+                                              reinterpret_cast<float4*>(a.next), a.out_fit, a.out_coll, a.sel, a.cpo,
+                                              n_big, n_big + n_small, sched);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
