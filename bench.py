@@ -336,7 +336,7 @@ def run_gpu(args):
                    "migration": f"{ELITES} elites NCCL all-gather every {MIGRATE_EVERY} generations, pipelined with the next generation on a side stream" if world > 1 else "none (1 island)",
                    "l2": "inputs larger than L2: population 2 x %.0f MiB ping-pong, voxel grid %d MiB" % (
                        P * W * 16 / 2 ** 20, (cfg["world"][0] * cfg["world"][1] * cfg["world"][2] // 8) >> 20 if cfg["n_voxel_obs"] else 0)},
-        "roofline": {"bound": "hbm", "kernel": "stream_kernel<GA> (tf_generation, TMA-staged)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "tf_generation (TMA-staged fused generation kernel: duo_kernel<GA> without an obstacle table, stream_kernel<GA> with one)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bpu * P * (W - 1),
                      "algorithmic_bytes_per_unit": bpu, "kernel_ms": gen_ms,

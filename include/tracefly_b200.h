@@ -299,8 +299,9 @@ int tf_selftest_sqrt(uint32_t first_bits, uint64_t count, uint64_t* mismatches_d
 /* Options.  TF_OPT_DISABLE_STREAM = 1 forces the LSU-path kernels even where the TMA-staged
  * kernels apply (W = 32 / 64, fixed length); both give bit-identical results. */
 #define TF_OPT_DISABLE_STREAM 1
-/* TF_OPT_STREAM_SCHEDULE: 0 (default) = the TMA-staged kernels evaluate two chromosomes per warp step (one
- * per half-warp), 1 = one chromosome per warp step.  Bit-identical results; kept for A/B measurements. */
+/* TF_OPT_STREAM_SCHEDULE: how the TMA-staged kernels walk a tile.  1 = one chromosome per warp step,
+ * 2 = two (one per half-warp, dynamic tile tickets), 0 (default) = the library picks per kernel variant.
+ * Bit-identical results either way; exposed for A/B measurements and the equivalence tests. */
 #define TF_OPT_STREAM_SCHEDULE 2
 int tf_set_option(int option, int value);
 /* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */

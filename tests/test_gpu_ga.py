@@ -197,7 +197,7 @@ def test_init_populations(tf):
 @pytest.mark.parametrize("W", [32, 64])
 @pytest.mark.parametrize("env_kind", ["none", "pf", "vox+dyn+haz"])
 def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind, P):
-    """The TMA-staged kernels (W = 32/64), in both schedules (two chromosomes per warp step / one), must give
+    """The TMA-staged kernels (W = 32/64), in both schedules (one chromosome per warp step / two), must give
     bit-identical results to the LSU-path kernels."""
     torch, L, B = tf
     rng = np.random.default_rng(W)
@@ -219,7 +219,7 @@ def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind, P):
     pop = B.init_walks(5, P, W, start=(32, 32, 32), lo=(0, 0, 0), hi=(63, 63, 63))
     ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=3, mutation_rate=0.5, n_elite=3)
     res = []
-    for disable, schedule in ((0, 0), (0, 1), (1, 0)):
+    for disable, schedule in ((0, 0), (0, 1), (0, 2), (1, 0)):
         L.set_option(L.OPT_DISABLE_STREAM, disable)
         L.set_option(L.OPT_STREAM_SCHEDULE, schedule)
         try:

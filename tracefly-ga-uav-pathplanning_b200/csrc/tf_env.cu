@@ -702,7 +702,7 @@ extern "C" int tf_selftest_sqrt(uint32_t first_bits, uint64_t count, uint64_t* m
 
 extern "C" int tf_set_option(int option, int value) {
     if (option == TF_OPT_DISABLE_STREAM) { tf::g_disable_stream = value != 0; return TF_OK; }
-    if (option == TF_OPT_STREAM_SCHEDULE && (value == 0 || value == 1)) { tf::g_stream_schedule = value; return TF_OK; }
+    if (option == TF_OPT_STREAM_SCHEDULE && value >= 0 && value <= 2) { tf::g_stream_schedule = value; return TF_OK; }
     return TF_ERR_INVALID;
 }
 

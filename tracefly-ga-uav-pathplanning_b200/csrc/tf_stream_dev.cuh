@@ -502,7 +502,11 @@ template <int NW, int SEM, bool VOX, int XF, bool GA>
 static int launch_stream(const StreamArgs& a) {
     const size_t smem = stream_smem_bytes(*a.e, a.W);
     const int T = tile_size_for(a.P);
-    if (g_stream_schedule == 1) {  // one chromosome per warp step, static tile assignment
+    // schedule: two chromosomes per warp step wherever there is no obstacle-table loop (measured faster on the
+    // voxel / hazard / moving-sphere variants); with a table loop the extra registers (104 vs 64) halve the
+    // occupancy and one chromosome per warp step stays ahead (cfg2: 56 us vs 71 us)
+    const bool duo = g_stream_schedule == 0 ? SEM == TF_SEM_NONE : g_stream_schedule == 2;
+    if (!duo) {  // one chromosome per warp step, static tile assignment
         auto kern = stream_kernel<NW, SEM, VOX, XF, GA>;
         if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int ntiles = (a.P + T - 1) / T;
