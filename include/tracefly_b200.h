@@ -277,6 +277,21 @@ int tf_replace_worst(float* pop_dev, float* fit_dev, const int32_t* worst_idx_de
  * population: fit_dev i32[P] = -len - #{i in [1, len-2] : path[i-1] != path[i+1]}. */
 int tf_fitness_gae(const float* pop_dev, const int32_t* lens_dev, int P, int W, int32_t* fit_dev, void* stream);
 
+/* ---- initial population of the shaped-obstacle GA ------------------------------ */
+/* `PathPlanner.find_path(dodge_strategy, height_variation)` ("GA_complex _PF.py":93-132) for n paths at once,
+ * one thread per path: from `source`, step by sign(destination - current) per axis (z biased by the path's
+ * height variation, PF:111-116); if the next point is an obstacle (PF:28-44 rules of `env`, evaluated in
+ * float64 like the reference) try the single dodge move instead, or stay (PF:118-129); stop at the
+ * destination or when a point repeats (PF:105-106).  `GeneticAlgorithm.initialize_population` (PF:181-188)
+ * is one call with n = population_size and the height variations it draws.
+ * paths64_dev: f64[n][cap][4] (x, y, z, 0), the layout tf_fitness_f64 reads; lens_dev: i32[n].
+ * A path that needs more than `cap` waypoints is cut at cap and counted in *overflow_dev (i32, device,
+ * caller-zeroed, may be NULL): the caller retries with a larger cap. */
+enum { TF_DODGE_UP = 0, TF_DODGE_DOWN = 1, TF_DODGE_LEFT = 2, TF_DODGE_RIGHT = 3, TF_DODGE_FORWARD = 4, TF_DODGE_BACKWARD = 5 };
+int tf_find_path_pf(const tf_env* env, const double source[3], const double destination[3],
+                    const int32_t* height_variation_dev, int n, int dodge, int cap, double* paths64_dev,
+                    int32_t* lens_dev, int32_t* overflow_dev, void* stream);
+
 /* ---- compact host format -------------------------------------------------- */
 /* int16[n][4] (x, y, z, pad) <-> f32[n][4]: lattice chromosomes at 8 B per waypoint for the PCIe leg.
  * Packing rounds to nearest and saturates; it is exact for integer coordinates in [-32768, 32767]. */

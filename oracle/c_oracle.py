@@ -240,6 +240,24 @@ def init_diagonal(start, end, wcap=0):
     return out[:n]
 
 
+DODGE_MOVES = {"up": (0, 0, 1), "down": (0, 0, -1), "left": (-1, 0, 0), "right": (1, 0, 0), "forward": (0, 1, 0),
+               "backward": (0, -1, 0)}
+
+
+def find_path_pf(env, source, destination, height_variations, dodge="up", cap=256):
+    """PF:93-132 for a batch of height variations -> (paths f64[n, cap, 4], lens i32[n], overflow count)."""
+    hv = np.ascontiguousarray(height_variations, np.int32)
+    n = len(hv)
+    paths = np.zeros((n, cap, 4), np.float64)
+    lens = np.zeros(n, np.int32)
+    over = np.zeros(1, np.int32)
+    d3 = lambda v: (C.c_double * 3)(*[float(x) for x in v])
+    obs64 = env.obs64 if env.obs64 is not None else _widen(env.obs)
+    lib().orc_find_path_pf(C.byref(env.c), _p(obs64), C.c_double(env.safety64), d3(source), d3(destination), _p(hv), n,
+                           d3(DODGE_MOVES[dodge]), cap, _p(paths), _p(lens), _p(over))
+    return paths, lens, int(over[0])
+
+
 def init_walks(seed, P, W, start, lo, hi, start_pp=None):
     pop = np.zeros((P, W, 4), np.float32)
     f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])

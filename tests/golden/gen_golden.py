@@ -336,10 +336,52 @@ def gen_evolve_pf(pf):
     print(f"evolve_pf_default.npz: {dt:.1f}s reference wall, lens {sorted(set(lens.tolist()))}")
 
 
+def gen_find_path_pf(pf):
+    """PF:93-132 PathPlanner.find_path on seeded PF environments: every dodge strategy, height variations
+    -2..1 (what PF:185 draws) and a few larger ones, integer and float endpoints, dense obstacle fields that
+    trigger the dodge and the loop guard."""
+    cases = []
+    scen = [  # (seed, bounds, n_obstacles, source, destination)
+        (0, ((0, 20), (0, 20), (0, 10)), 10, (0, 0, 0), (15, 15, 8)),          # PF:256-266 scenario
+        (1, ((0, 20), (0, 20), (0, 10)), 60, (0, 0, 0), (19, 19, 9)),          # dense: dodges
+        (2, ((0, 12), (0, 12), (0, 6)), 80, (1, 1, 1), (11, 10, 5)),           # very dense: loop guard / stuck
+        (3, ((0, 40), (0, 40), (0, 20)), 120, (39, 2, 1), (0, 37, 18)),        # negative directions, long
+        (4, ((0, 20), (0, 20), (0, 10)), 30, (3, 3, 3), (3, 3, 3)),            # source == destination
+        (5, ((0, 20), (0, 20), (0, 10)), 40, (0.5, 0.25, 0.0), (12.5, 9.25, 6.0)),  # float lattice offsets
+    ]
+    for seed, bounds, nobs, src, dst in scen:
+        env = pf_seeded_obstacles(pf, seed, bounds, nobs)
+        planner = pf.PathPlanner(src, dst, env)
+        for dodge in ("up", "down", "left", "right", "forward", "backward"):
+            for hv in (-2, -1, 0, 1, 3):
+                path = planner.find_path(dodge_strategy=dodge, height_variation=hv)
+                cases.append(dict(scen=seed, dodge=dodge, hv=hv, path=[[float(v) for v in p] for p in path]))
+    Wmax = max(len(c["path"]) for c in cases)
+    wp = np.zeros((len(cases), Wmax, 3))
+    lens = np.zeros(len(cases), np.int32)
+    for i, c in enumerate(cases):
+        lens[i] = len(c["path"])
+        wp[i, :lens[i]] = np.array(c["path"], np.float64)
+    envs = {}
+    for seed, bounds, nobs, src, dst in scen:
+        env = pf_seeded_obstacles(pf, seed, bounds, nobs)
+        envs[f"pos_{seed}"] = np.array([o["position"] for o in env.obstacles], np.float64)
+        envs[f"size_{seed}"] = np.array([o["size"] for o in env.obstacles], np.float64)
+        envs[f"kind_{seed}"] = np.array([KINDS.index(o["shape"]) for o in env.obstacles], np.int32)
+        envs[f"src_{seed}"] = np.array(src, np.float64)
+        envs[f"dst_{seed}"] = np.array(dst, np.float64)
+    meta = dict(META, ref="PF:93-132", scenarios=[s[0] for s in scen])
+    np.savez_compressed(os.path.join(HERE, "find_path_pf.npz"), wp=wp, lens=lens,
+                        scen=np.array([c["scen"] for c in cases], np.int32),
+                        hv=np.array([c["hv"] for c in cases], np.int32),
+                        dodge=np.array([c["dodge"] for c in cases]), meta=np.array(json.dumps(meta)), **envs)
+    print(f"find_path_pf.npz: {len(cases)} paths, lens {int(lens.min())}..{int(lens.max())}")
+
+
 def main():
     hr = ref_loader.load_hr()
     pf = ref_loader.load_pf()
-    which = set(sys.argv[1:]) or {"fitness", "evolve", "gae"}
+    which = set(sys.argv[1:]) or {"fitness", "evolve", "gae", "find_path"}
     if "fitness" in which:
         gen_fitness_hr(hr)
         gen_fitness_pf(pf)
@@ -359,6 +401,8 @@ def main():
         gen_evolve_pf(pf)
     if "gae" in which:
         gen_run_gae()
+    if "find_path" in which:
+        gen_find_path_pf(pf)
 
 
 

@@ -86,6 +86,7 @@ _SIGS = {
     "tf_last_cuda_error": (_i, []),
     "tf_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i64)]),
     "tf_philox4x32_10": (None, [_u32, _u32, _u32, _u32, _u32, _u32, C.POINTER(_u32)]),
+    "tf_find_path_pf": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "tf_selftest_sqrt": (_i, [_u32, _u64, _vp, _vp]),
     "tf_set_option": (_i, [_i, _i]),
     "tf_launch_count": (_i64, []),
@@ -137,6 +138,7 @@ def philox(key0, key1, c0, c1, c2, c3):
     return [int(v) for v in out]
 
 
+DODGE = {"up": 0, "down": 1, "left": 2, "right": 3, "forward": 4, "backward": 5}
 OPT_DISABLE_STREAM = 1
 OPT_STREAM_SCHEDULE = 2
 

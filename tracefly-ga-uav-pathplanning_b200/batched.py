@@ -293,6 +293,29 @@ def point_query_f64(points, env):
     return coll.cpu().numpy().astype(bool), dn.cpu().numpy()
 
 
+def find_path_pf(env, source, destination, height_variations, dodge="up", cap=64, max_cap=1 << 16):
+    """`PathPlanner.find_path` (PF:93-132) for a batch of height variations: one launch, one thread per path.
+    -> (paths f64[n, cap, 4] cuda, lens i32[n] cuda).  The capacity is doubled (and the launch repeated)
+    until every path fits."""
+    _require_cuda()
+    hv = torch.as_tensor(np.ascontiguousarray(height_variations, np.int32)).cuda()
+    n = hv.numel()
+    src = (C.c_double * 3)(*[float(v) for v in source])
+    dst = (C.c_double * 3)(*[float(v) for v in destination])
+    over = torch.zeros(1, dtype=torch.int32, device="cuda")
+    while True:
+        paths = torch.empty((n, cap, 4), dtype=torch.float64, device="cuda")
+        lens = torch.empty(n, dtype=torch.int32, device="cuda")
+        over.zero_()
+        check(lib.tf_find_path_pf(env.handle, src, dst, _ptr(hv), n, L.DODGE[dodge], cap, _ptr(paths), _ptr(lens), _ptr(over),
+                                  _stream()), "tf_find_path_pf")
+        if n == 0 or int(over.item()) == 0:
+            return paths, lens
+        if cap >= max_cap:
+            raise RuntimeError(f"find_path_pf: a path needs more than {max_cap} waypoints")
+        cap *= 2
+
+
 # ------------------------------------------------------------------------------------ ranking
 class TopK:
     """Reusable top-k plan (owns the workspace): order = (fitness desc, index asc) — the stable

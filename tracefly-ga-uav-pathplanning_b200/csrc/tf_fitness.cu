@@ -86,6 +86,45 @@ __global__ void point_query_f64_kernel(const __grid_constant__ EnvDev e, const d
     if (dnear) dnear[i] = best;
 }
 
+// PF:93-132 `PathPlanner.find_path`, one thread per path (the walk is sequential, the paths are independent).
+__device__ __forceinline__ double sign_d(double v) { return v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0); }
+__global__ void find_path_pf_kernel(const __grid_constant__ EnvDev e, double sx, double sy, double sz, double tx,
+                                    double ty, double tz, const int32_t* __restrict__ hv, int n, double mx, double my,
+                                    double mz, int cap, double* __restrict__ paths, int32_t* __restrict__ lens,
+                                    int32_t* __restrict__ overflow) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    double* out = paths + (size_t)p * cap * 4;
+    const double bias = (double)hv[p];
+    double cx = sx, cy = sy, cz = sz;
+    int len = 1;
+    out[0] = cx; out[1] = cy; out[2] = cz; out[3] = 0.0;
+    while (!(cx == tx && cy == ty && cz == tz)) {  // PF:97
+        const double nx = __dadd_rn(cx, sign_d(__dsub_rn(tx, cx))), ny = __dadd_rn(cy, sign_d(__dsub_rn(ty, cy))),
+                     nz = __dadd_rn(cz, sign_d(__dadd_rn(__dsub_rn(tz, cz), bias)));  // PF:111-116
+        bool hit;
+        double dn;
+        point_eval_f64(e, nx, ny, nz, hit, dn);
+        if (hit) {  // PF:100-101, 118-129: one dodge move, or stay put
+            const double qx = __dadd_rn(cx, mx), qy = __dadd_rn(cy, my), qz = __dadd_rn(cz, mz);
+            point_eval_f64(e, qx, qy, qz, hit, dn);
+            if (!hit) { cx = qx; cy = qy; cz = qz; }
+        } else {
+            cx = nx; cy = ny; cz = nz;
+        }
+        bool seen = false;  // PF:105-106 loop guard
+        for (int i = len - 1; i >= 0 && !seen; --i) seen = out[4 * i] == cx && out[4 * i + 1] == cy && out[4 * i + 2] == cz;
+        if (seen) break;
+        if (len == cap) {
+            if (overflow) atomicAdd(overflow, 1);
+            break;
+        }
+        out[4 * len] = cx; out[4 * len + 1] = cy; out[4 * len + 2] = cz; out[4 * len + 3] = 0.0;
+        ++len;
+    }
+    lens[p] = len;
+}
+
 __global__ void __launch_bounds__(128)
 fitness_f64_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
                    const double* __restrict__ pop, const int32_t* __restrict__ lens, int P, int W,
@@ -180,6 +219,23 @@ extern "C" int tf_point_query_f64(const tf_env* env, const double* pts64_dev, in
     if (rc != TF_OK) return rc;
     if (n == 0) return TF_OK;
     point_query_f64_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->d, pts64_dev, n, collide_dev, dnear_dev);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+
+extern "C" int tf_find_path_pf(const tf_env* env, const double source[3], const double destination[3],
+                               const int32_t* height_variation_dev, int n, int dodge, int cap, double* paths64_dev,
+                               int32_t* lens_dev, int32_t* overflow_dev, void* stream) {
+    static const double kMoves[6][3] = {{0, 0, 1}, {0, 0, -1}, {-1, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, -1, 0}};  // PF:119-126
+    if (!env || !source || !destination || !height_variation_dev || !paths64_dev || !lens_dev) return TF_ERR_INVALID;
+    if (n < 0 || cap < 1 || dodge < 0 || dodge > 5) return TF_ERR_INVALID;
+    if (env->d.n_dyn > 0 || env->d.bricks || env->d.hazard) return TF_ERR_UNSUPPORTED;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    if (n == 0) return TF_OK;
+    find_path_pf_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(
+        env->d, source[0], source[1], source[2], destination[0], destination[1], destination[2], height_variation_dev, n,
+        kMoves[dodge][0], kMoves[dodge][1], kMoves[dodge][2], cap, paths64_dev, lens_dev, overflow_dev);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

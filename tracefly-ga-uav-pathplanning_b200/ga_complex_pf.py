@@ -14,9 +14,11 @@ Upstream behaviour that is reproduced on purpose
     mutate are consumed — we consume the same draws and launch the same G sweeps;
   * `select_parents` sorts in place, stably, on the PREVIOUS sweep's fitness (zeros the first time);
   * no zero-distance guard: an all-identical path scores inf (PF:163).
-The random obstacle generator (PF:17-26) and the greedy `PathPlanner` (PF:89-132, sequential, used only to
-seed the population — SURVEY §8f-1) are host code that draws from `random` / `np.random` in upstream's
-order; every obstacle test they make is a device point query.  Plotting helpers are not provided.
+    PathPlanner.find_path                                    PF:93-107   tf_find_path_pf (one thread per path);
+    GeneticAlgorithm.initialize_population                   PF:181-188  ONE launch for the whole population
+The random obstacle generator (PF:17-26) is host code that draws from `random` / `np.random` in upstream's
+order.  `find_next_step` / `dodge_obstacle` stay available as single-step host methods (their obstacle test
+is a device point query).  Plotting helpers are not provided.
 """
 import random
 
@@ -88,15 +90,24 @@ class PathPlanner:
         shifted = tuple(c + d for c, d in zip(current, _DODGES[dodge_strategy]))
         return current if self.environment.is_obstacle(shifted) else shifted
 
+    def find_paths(self, dodge_strategy, height_variations):
+        """`find_path` for every entry of `height_variations`: one tf_find_path_pf launch."""
+        if dodge_strategy not in _DODGES:
+            raise KeyError(dodge_strategy)                      # upstream: moves[dodge_strategy]
+        paths, lens = B.find_path_pf(self.environment.device_env(), self.source, self.destination,
+                                     [int(v) for v in height_variations], dodge_strategy)
+        rows, counts = paths.cpu().numpy(), lens.cpu().tolist()
+        whole = all(float(v).is_integer() for v in tuple(self.source) + tuple(self.destination))
+        out = []
+        for row, count in zip(rows, counts):
+            pts = row[:count, :3]
+            trail = [tuple(int(v) for v in q) for q in pts] if whole else [tuple(float(v) for v in q) for q in pts]
+            trail[0] = self.source                              # upstream keeps the caller's tuple first
+            out.append(trail)
+        return out
+
     def find_path(self, dodge_strategy, height_variation=0):
-        here, trail = self.source, [self.source]
-        while here != self.destination:
-            ahead = self.find_next_step(here, self.destination, height_variation)
-            here = self.dodge_obstacle(here, dodge_strategy) if self.environment.is_obstacle(ahead) else ahead
-            if here in trail:        # upstream's loop guard
-                break
-            trail.append(here)
-        return trail
+        return self.find_paths(dodge_strategy, [height_variation])[0]
 
 
 class Path:
@@ -121,10 +132,11 @@ class GeneticAlgorithm:
         self.population = self.initialize_population()
 
     def initialize_population(self):
-        # one np.random.randint(-2, 2) per individual, drawn in order
+        # one np.random.randint(-2, 2) per individual, drawn in upstream's order; the walks themselves consume
+        # no random numbers, so all of them run in one launch
+        lifts = [np.random.randint(-2, 2) for _ in range(self.population_size)]
         planner = PathPlanner(self.source, self.destination, self.environment)
-        return [Path(planner.find_path(dodge_strategy="up", height_variation=np.random.randint(-2, 2)))
-                for _ in range(self.population_size)]
+        return [Path(trail) for trail in planner.find_paths("up", lifts)]
 
     def select_parents(self):
         self.population.sort(key=lambda p: p.fitness, reverse=True)
