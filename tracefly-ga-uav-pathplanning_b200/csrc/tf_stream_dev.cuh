@@ -267,8 +267,10 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 // are bit-identical (tests run both through TF_OPT_STREAM_SCHEDULE).
 // Tile bookkeeping: lanes 0-15 own children [0, T/2) of the tile, lanes 16-31 own [T/2, T); pair j =
 // children j and T/2 + j = lanes j and 16 + j, so every total ends in the half where its owner sits.
+// XF 1 (hazard map / moving spheres): 2 CTAs / SM = up to 128 registers; at 3 (80 registers) the candidate-list
+// loop spilled 250 bytes and cfg4 ran 8 % slower
 template <int NW, int SEM, bool VOX, int XF, bool GA>
-__global__ void __launch_bounds__(kBlockThreads, (XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? 3 : 0))
+__global__ void __launch_bounds__(kBlockThreads, (XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? 2 : 0))
 duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
            const __grid_constant__ tf_ga_params ga, const float4* __restrict__ pop,
            const float* __restrict__ fit, const int32_t* __restrict__ top_idx,
