@@ -230,7 +230,7 @@ def run_gpu(args):
         # the per-step events bracket ONLY the dominant kernel (tf_generation) for the roofline
         island.ops.rank(island.fit, island.top)
         gen_ev[i][0].record(stream)
-        island.ops.generation(island.pop, island.fit, island.top, island.ga, island.seed, island.gen, island.nxt, island.nfit)
+        island.launch_generation()
         gen_ev[i][1].record(stream)
         island.pop, island.nxt = island.nxt, island.pop
         island.fit, island.nfit = island.nfit, island.fit

@@ -318,6 +318,10 @@ int tf_selftest_sqrt(uint32_t first_bits, uint64_t count, uint64_t* mismatches_d
  * 2 = two (one per half-warp, dynamic tile tickets), 0 (default) = the library picks per kernel variant.
  * Bit-identical results either way; exposed for A/B measurements and the equivalence tests. */
 #define TF_OPT_STREAM_SCHEDULE 2
+/* TF_OPT_RESERVE_SMS: number of SMs (0 = none, at most half) that the persistent, dynamically scheduled
+ * kernels leave unoccupied, so that kernels on other streams (elite selection, NCCL) run beside them instead
+ * of waiting for the whole grid to drain.  Read at launch time. */
+#define TF_OPT_RESERVE_SMS 3
 int tf_set_option(int option, int value);
 /* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
 int64_t tf_launch_count(void);

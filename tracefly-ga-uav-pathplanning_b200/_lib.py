@@ -141,6 +141,7 @@ def philox(key0, key1, c0, c1, c2, c3):
 DODGE = {"up": 0, "down": 1, "left": 2, "right": 3, "forward": 4, "backward": 5}
 OPT_DISABLE_STREAM = 1
 OPT_STREAM_SCHEDULE = 2
+OPT_RESERVE_SMS = 3
 
 
 def set_option(option, value):

@@ -16,6 +16,7 @@ thread_local int g_last_cuda_error = 0;
 long long g_launch_count = 0;
 int g_disable_stream = 0;
 int g_stream_schedule = 0;
+int g_reserve_sms = 0;
 static int g_sm_count = 0;
 static int g_dev_checked = 0;
 
@@ -702,6 +703,7 @@ extern "C" int tf_selftest_sqrt(uint32_t first_bits, uint64_t count, uint64_t* m
 
 extern "C" int tf_set_option(int option, int value) {
     if (option == TF_OPT_DISABLE_STREAM) { tf::g_disable_stream = value != 0; return TF_OK; }
+    if (option == TF_OPT_RESERVE_SMS && value >= 0) { tf::g_reserve_sms = value; return TF_OK; }
     if (option == TF_OPT_STREAM_SCHEDULE && value >= 0 && value <= 2) { tf::g_stream_schedule = value; return TF_OK; }
     return TF_ERR_INVALID;
 }

@@ -541,7 +541,9 @@ static int launch_stream(const StreamArgs& a) {
         n_small = (a.P - n_big * T + Ts - 1) / Ts;
         sched = sched_slot();
         if (sched == nullptr) return TF_ERR_NOMEM;
-        grid = sm_count() * max(occ, 1);
+        // TF_OPT_RESERVE_SMS: leave some SMs to kernels of other streams (the island model's elite exchange
+        // runs beside the generation; a full persistent grid would hold every CTA slot until it ends)
+        grid = max(sm_count() - g_reserve_sms, sm_count() / 2) * max(occ, 1);
     }
     kern<<<grid, kBlockThreads, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
                                               a.top_idx, a.tape, a.seed, a.gen, a.P, T,

@@ -38,6 +38,7 @@ class CudaOps:
         self.topk_elite = B.TopK(P, E) if E else None
         self.worst_set = B.SelectSet(P, n_worst) if n_worst else None
         self.side = torch.cuda.Stream() if n_worst else None
+        self.reserve_sms = 8
 
     def fitness(self, pop):
         return self.B.fitness_batch(pop, None, self.env, self.params, want_collisions=False)[0]
@@ -45,9 +46,17 @@ class CudaOps:
     def rank(self, fit, out):
         return self.topk_rank(fit, out=out)
 
-    def generation(self, pop, fit, top, ga, seed, gen, out_pop, out_fit):
-        self.B.generation(self.env, pop, fit, top, ga, self.params, seed=seed, generation=gen, out_pop=out_pop,
-                          out_fit=out_fit)
+    def generation(self, pop, fit, top, ga, seed, gen, out_pop, out_fit, beside_exchange=False):
+        # while an elite exchange is in flight on the side stream, the persistent generation kernel leaves a
+        # few SMs free for it (it would otherwise hold every CTA slot until it ends)
+        if beside_exchange:
+            L.set_option(L.OPT_RESERVE_SMS, self.reserve_sms)
+        try:
+            self.B.generation(self.env, pop, fit, top, ga, self.params, seed=seed, generation=gen, out_pop=out_pop,
+                              out_fit=out_fit)
+        finally:
+            if beside_exchange:
+                L.set_option(L.OPT_RESERVE_SMS, 0)
 
     def elites(self, fit, out):
         return self.topk_elite(fit, out=out)
@@ -117,11 +126,19 @@ class IslandGA:
     def step(self):
         """rank -> select/crossover/mutate + fitness (fused); then the migration schedule."""
         self.ops.rank(self.fit, self.top)
-        self.ops.generation(self.pop, self.fit, self.top, self.ga, self.seed, self.gen, self.nxt, self.nfit)
+        self.launch_generation()
         self.pop, self.nxt = self.nxt, self.pop
         self.fit, self.nfit = self.nfit, self.fit
         self.gen += 1
         self.after_generation()
+
+    def launch_generation(self):
+        """The fused generation kernel of the current population into the spare buffers."""
+        if self._pending and isinstance(self.ops, CudaOps):
+            self.ops.generation(self.pop, self.fit, self.top, self.ga, self.seed, self.gen, self.nxt, self.nfit,
+                                beside_exchange=True)
+        else:
+            self.ops.generation(self.pop, self.fit, self.top, self.ga, self.seed, self.gen, self.nxt, self.nfit)
 
     def after_generation(self):
         if self.world <= 1 or self.E == 0 or self.interval <= 0:
