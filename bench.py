@@ -259,16 +259,17 @@ def run_gpu(args):
     #      in flight so the D2H leg of step n overlaps the H2D leg of step n+1.
     e2e = None
     e2e_compact = None
+    e2e_padded = None
     if not args.no_e2e:
         del island.nxt, island.nfit          # make room: the stepper owns its own device buffers
         torch.cuda.empty_cache()
 
         def run_e2e(fmt, steps):
             stepper = B.HostStepper(env, P, W, ga, params, fmt=fmt, depth=2)
-            hdt = torch.float32 if fmt == "f32" else torch.int16
-            hosts = [torch.empty((P, W, 4), dtype=hdt).pin_memory() for _ in range(2)]
+            hdt, hc = B.HostStepper._HOST[fmt]
+            hosts = [torch.empty((P, W, hc), dtype=hdt).pin_memory() for _ in range(2)]
             for h in hosts:
-                h.copy_(island.pop.to(hdt) if fmt == "i16" else island.pop)
+                h.copy_(island.pop[..., :hc].to(hdt))
             sync_all()
             tickets = []
             checksum = 0.0
@@ -297,13 +298,15 @@ def run_gpu(args):
             torch.cuda.empty_cache()
             return {"value": units_per_step * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": ms / steps, "steps": steps,
-                    "host_format": "float32[P,W,4]" if fmt == "f32" else "int16[P,W,4] (lattice chromosomes)",
+                    "host_format": {"f32": "float32[P,W,4] (the device layout)", "xyz": "float32[P,W,3] (the reference's 3-tuples as an array)",
+                                    "i16": "int16[P,W,4] (lattice chromosomes)"}[fmt],
                     "what": "pinned host population in -> tf_fitness + tf_rank_topk + tf_generation -> host fitness "
                             "vector + next population out; 2 requests in flight (D2H of step n overlaps H2D of step n+1); "
                             "wall clock around the whole loop incl. the final drain"}
 
         e2e_steps = max(4, min(args.steps, 10))
-        e2e = run_e2e("f32", e2e_steps)
+        e2e = run_e2e("xyz", e2e_steps)
+        e2e_padded = run_e2e("f32", e2e_steps)
         e2e_compact = run_e2e("i16", e2e_steps)
 
     if rank != 0:
@@ -346,6 +349,7 @@ def run_gpu(args):
     }
     if e2e:
         line["e2e"] = e2e
+        line["e2e_padded_host_format"] = e2e_padded
         line["e2e_compact_host_format"] = e2e_compact
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.workload, seconds=args.cpu_seconds)

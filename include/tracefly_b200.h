@@ -296,6 +296,10 @@ int tf_find_path_pf(const tf_env* env, const double source[3], const double dest
 /* int16[n][4] (x, y, z, pad) <-> f32[n][4]: lattice chromosomes at 8 B per waypoint for the PCIe leg.
  * Packing rounds to nearest and saturates; it is exact for integer coordinates in [-32768, 32767]. */
 int tf_unpack_i16(const int16_t* in_dev, float* pop_dev, int64_t n_waypoints, void* stream);
+/* f32[n][3] (x, y, z) <-> f32[n][4]: the reference's waypoints are 3-tuples (HR:33-36), so a caller's array
+ * form is [P][W][3]; 12 B per waypoint on the PCIe leg, the pad lane is written as 0. */
+int tf_unpack_xyz(const float* in_dev, float* pop_dev, int64_t n_waypoints, void* stream);
+int tf_pack_xyz(const float* pop_dev, float* out_dev, int64_t n_waypoints, void* stream);
 int tf_pack_i16(const float* pop_dev, int16_t* out_dev, int64_t n_waypoints, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------ */

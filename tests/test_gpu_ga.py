@@ -236,7 +236,7 @@ def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind, P):
             assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("fmt", ["f32", "i16"])
+@pytest.mark.parametrize("fmt", ["f32", "xyz", "i16"])
 def test_host_stepper_round_trip(tf, fmt):
     """Host-array API: pinned population in -> fitness + next population out equals the device API."""
     torch, L, B = tf
@@ -248,8 +248,9 @@ def test_host_stepper_round_trip(tf, fmt):
     prm = L.default_params(dist_zero_guard=0)
     pops = [B.init_walks(s, P, W, start=(32, 32, 32), lo=(0, 0, 0), hi=(63, 63, 63)) for s in (1, 2, 3)]
     stepper = B.HostStepper(env, P, W, ga, prm, fmt=fmt, depth=2)
-    hdt = torch.float32 if fmt == "f32" else torch.int16
-    hosts = [p.to(hdt).cpu().pin_memory() for p in pops]
+    hdt = torch.int16 if fmt == "i16" else torch.float32
+    hc = 3 if fmt == "xyz" else 4
+    hosts = [p[..., :hc].to(hdt).contiguous().cpu().pin_memory() for p in pops]
     tickets = [stepper.submit(hosts[0], seed=5, generation=0), stepper.submit(hosts[1], seed=5, generation=1)]
     got = []
     for i in range(3):
@@ -262,9 +263,9 @@ def test_host_stepper_round_trip(tf, fmt):
         top = B.rank_topk(fit, 2)
         nxt, nfit, *_ = B.generation(env, pop, fit, top, ga, prm, seed=5, generation=g)
         assert torch.equal(fit.cpu(), fit_h)
-        assert torch.equal(nxt.to(hdt).cpu(), next_h)
+        assert torch.equal(nxt[..., :hc].to(hdt).cpu(), next_h)
     h2d, d2h = stepper.bytes_per_step()
-    assert h2d == P * W * 4 * (4 if fmt == "f32" else 2)
+    assert h2d == P * W * {"f32": 16, "xyz": 12, "i16": 8}[fmt] and d2h == h2d + 4 * P
 
 
 @pytest.mark.parametrize("P,k", [(1, 1), (5000, 37), (300_000, 1024), (1_000_003, 7168), (70_000, 69_999)])

@@ -86,6 +86,8 @@ _SIGS = {
     "tf_last_cuda_error": (_i, []),
     "tf_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i64)]),
     "tf_philox4x32_10": (None, [_u32, _u32, _u32, _u32, _u32, _u32, C.POINTER(_u32)]),
+    "tf_unpack_xyz": (_i, [_vp, _vp, _i64, _vp]),
+    "tf_pack_xyz": (_i, [_vp, _vp, _i64, _vp]),
     "tf_find_path_pf": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "tf_selftest_sqrt": (_i, [_u32, _u64, _vp, _vp]),
     "tf_set_option": (_i, [_i, _i]),

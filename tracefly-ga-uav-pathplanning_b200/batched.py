@@ -540,18 +540,21 @@ class HostStepper:
     the reference's process looks like): each `submit` copies a pinned host population to the GPU,
     runs fitness -> rank -> fused generation there, and copies the fitness vector and the next
     population back.  `depth` requests are in flight on separate streams, so the D2H leg of step n
-    overlaps the H2D leg of step n+1 (PCIe is full duplex).  fmt="i16" moves lattice chromosomes as
-    int16[P, W, 4] (8 B per waypoint) and converts on the device (tf_unpack_i16 / tf_pack_i16)."""
+    overlaps the H2D leg of step n+1 (PCIe is full duplex).  Host formats: "xyz" float32[P, W, 3] (the
+    reference's 3-tuples as an array, 12 B per waypoint; tf_unpack_xyz / tf_pack_xyz), "f32" float32[P, W, 4]
+    (the device layout, 16 B), "i16" int16[P, W, 4] (lattice chromosomes, 8 B; tf_unpack_i16 / tf_pack_i16)."""
+
+    _HOST = {"f32": (torch.float32, 4), "xyz": (torch.float32, 3), "i16": (torch.int16, 4)}
 
     def __init__(self, env, P, W, ga=None, params=None, fmt="f32", depth=2, device="cuda"):
         _require_cuda()
-        if fmt not in ("f32", "i16"):
-            raise ValueError("fmt must be 'f32' or 'i16'")
+        if fmt not in self._HOST:
+            raise ValueError("fmt must be 'f32', 'xyz' or 'i16'")
         self.env, self.P, self.W, self.fmt = env, P, W, fmt
         self.ga = ga or L.default_ga_params()
         self.params = params or L.default_params(dist_zero_guard=1 if env.semantics != L.SEM_PF else 0)
         k = max(min(self.ga.n_elite, P), min(self.ga.n_top, P) if self.ga.selection == L.SEL_TRUNCATION else 1, 1)
-        hdt = torch.float32 if fmt == "f32" else torch.int16
+        hdt, hc = self._HOST[fmt]
         self.slots = []
         for _ in range(depth):
             s = dict(stream=torch.cuda.Stream(), pop=torch.empty((P, W, 4), dtype=torch.float32, device=device),
@@ -560,19 +563,20 @@ class HostStepper:
                      nfit=torch.empty(P, dtype=torch.float32, device=device),
                      top=torch.empty(k, dtype=torch.int32, device=device), topk=TopK(P, k, device=device),
                      host_fit=torch.empty(P, dtype=torch.float32).pin_memory(),
-                     host_next=torch.empty((P, W, 4), dtype=hdt).pin_memory(), busy=False)
-            if fmt == "i16":
-                s["stage_in"] = torch.empty((P, W, 4), dtype=torch.int16, device=device)
-                s["stage_out"] = torch.empty((P, W, 4), dtype=torch.int16, device=device)
+                     host_next=torch.empty((P, W, hc), dtype=hdt).pin_memory(), busy=False)
+            if fmt != "f32":
+                s["stage_in"] = torch.empty((P, W, hc), dtype=hdt, device=device)
+                s["stage_out"] = torch.empty((P, W, hc), dtype=hdt, device=device)
             self.slots.append(s)
         self._n = 0
 
     def bytes_per_step(self):
-        e = 4 if self.fmt == "f32" else 2
-        return self.P * self.W * 4 * e, self.P * self.W * 4 * e + self.P * 4
+        hdt, hc = self._HOST[self.fmt]
+        row = self.P * self.W * hc * (4 if hdt == torch.float32 else 2)
+        return row, row + self.P * 4
 
     def submit(self, host_pop, seed=0, generation=0):
-        """host_pop: pinned CPU tensor [P, W, 4] (float32, or int16 when fmt='i16').  Returns a ticket."""
+        """host_pop: pinned CPU tensor in the stepper's host format.  Returns a ticket."""
         s = self.slots[self._n % len(self.slots)]
         if s["busy"]:
             raise RuntimeError("HostStepper: collect the oldest result before submitting more work")
@@ -582,7 +586,8 @@ class HostStepper:
                 s["pop"].copy_(host_pop, non_blocking=True)
             else:
                 s["stage_in"].copy_(host_pop, non_blocking=True)
-                check(lib.tf_unpack_i16(_ptr(s["stage_in"]), _ptr(s["pop"]), n4, _stream()), "tf_unpack_i16")
+                unpack = lib.tf_unpack_i16 if self.fmt == "i16" else lib.tf_unpack_xyz
+                check(unpack(_ptr(s["stage_in"]), _ptr(s["pop"]), n4, _stream()), "tf_unpack")
             fitness_batch(s["pop"], None, self.env, self.params, out=s["fit"], want_collisions=False)
             s["topk"](s["fit"], out=s["top"])
             check(lib.tf_generation(self.env.handle, _ptr(s["pop"]), _ptr(s["fit"]), _ptr(s["top"]), None, seed,
@@ -592,7 +597,8 @@ class HostStepper:
             if self.fmt == "f32":
                 s["host_next"].copy_(s["nxt"], non_blocking=True)
             else:
-                check(lib.tf_pack_i16(_ptr(s["nxt"]), _ptr(s["stage_out"]), n4, _stream()), "tf_pack_i16")
+                pack = lib.tf_pack_i16 if self.fmt == "i16" else lib.tf_pack_xyz
+                check(pack(_ptr(s["nxt"]), _ptr(s["stage_out"]), n4, _stream()), "tf_pack")
                 s["host_next"].copy_(s["stage_out"], non_blocking=True)
         s["busy"] = True
         self._n += 1

@@ -21,9 +21,48 @@ __global__ void pack_i16_kernel(const float4* __restrict__ in, short4* __restric
     }
 }
 
+// (x, y, z) triples <-> the device's float4 waypoints: what a caller holding the reference's 3-tuples as a
+// float32[P, W, 3] array sends; 12 B per waypoint over PCIe instead of 16
+__global__ void unpack_xyz_kernel(const float* __restrict__ in, float4* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = make_float4(in[3 * i], in[3 * i + 1], in[3 * i + 2], 0.0f);
+}
+__global__ void pack_xyz_kernel(const float4* __restrict__ in, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = in[i];
+        out[3 * i] = v.x;
+        out[3 * i + 1] = v.y;
+        out[3 * i + 2] = v.z;
+    }
+}
+
 }  // namespace tf
 
 using namespace tf;
+
+extern "C" int tf_unpack_xyz(const float* in_dev, float* pop_dev, int64_t n_waypoints, void* stream) {
+    if (!in_dev || !pop_dev || n_waypoints < 0) return TF_ERR_INVALID;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    if (n_waypoints == 0) return TF_OK;
+    const int64_t want = (n_waypoints + 255) / 256, cap = (int64_t)sm_count() * 16;
+    unpack_xyz_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        in_dev, reinterpret_cast<float4*>(pop_dev), (size_t)n_waypoints);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+
+extern "C" int tf_pack_xyz(const float* pop_dev, float* out_dev, int64_t n_waypoints, void* stream) {
+    if (!pop_dev || !out_dev || n_waypoints < 0) return TF_ERR_INVALID;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    if (n_waypoints == 0) return TF_OK;
+    const int64_t want = (n_waypoints + 255) / 256, cap = (int64_t)sm_count() * 16;
+    pack_xyz_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(pop_dev), out_dev, (size_t)n_waypoints);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
 
 extern "C" int tf_unpack_i16(const int16_t* in_dev, float* pop_dev, int64_t n_waypoints, void* stream) {
     if (!in_dev || !pop_dev || n_waypoints < 0) return TF_ERR_INVALID;
