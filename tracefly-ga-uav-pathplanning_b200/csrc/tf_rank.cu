@@ -91,20 +91,20 @@ constexpr int kSmallItems = 8;
 constexpr int kSmallTile = kRankThreads * kSmallItems;
 constexpr int kSmallKMax = 16;
 
-template <typename Key, typename T>
-__global__ void __launch_bounds__(kRankThreads)
-topk_small_kernel(const T* __restrict__ values, const Key* __restrict__ keys_in, int n, int k, int worst,
-                  Key* __restrict__ keys_out, int32_t* __restrict__ idx_out) {
-    __shared__ Key wbest[kRankThreads / 32];
-    __shared__ Key winner;
-    Key mine[kSmallItems];
-    const int base = blockIdx.x * kSmallTile;
+template <typename Key>
+__device__ __forceinline__ Key load_key_cg(const Key* p) {  // L1-bypassing read of a key another CTA wrote
+    Key k;
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>(p);
+    unsigned long long* o = reinterpret_cast<unsigned long long*>(&k);
 #pragma unroll
-    for (int i = 0; i < kSmallItems; ++i) {
-        const int g = base + i * kRankThreads + threadIdx.x;
-        mine[i] = Key::pad();
-        if (g < n) mine[i] = values ? Key::make(values[g], (uint32_t)g, worst != 0) : keys_in[g];
-    }
+    for (int i = 0; i < (int)(sizeof(Key) / 8); ++i) o[i] = __ldcg(w + i);
+    return k;
+}
+
+// k rounds of block-wide arg-min over the keys in `mine`; round r's winner goes to idx_out[r] or keys_out[r]
+template <typename Key>
+__device__ __forceinline__ void small_rounds(Key (&mine)[kSmallItems], int k, int worst, Key* keys_out, int32_t* idx_out,
+                                             Key* wbest, Key* winner) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int r = 0; r < k; ++r) {
         Key best = mine[0];
@@ -128,17 +128,54 @@ topk_small_kernel(const T* __restrict__ values, const Key* __restrict__ keys_in,
                 if (o < b) b = o;
             }
             if (lane == 0) {
-                winner = b;
+                *winner = b;
                 if (idx_out) idx_out[r] = b.is_pad() ? -1 : (int32_t)b.index(worst != 0);
-                else keys_out[(size_t)blockIdx.x * k + r] = b;
+                else keys_out[r] = b;
             }
         }
         __syncthreads();
-        const Key w = winner;
+        const Key w = *winner;
 #pragma unroll
         for (int i = 0; i < kSmallItems; ++i)
             if (mine[i] == w) mine[i] = Key::pad();  // keys are unique: exactly one owner retires it
     }
+}
+
+// `done` != nullptr: single-launch form.  Every CTA leaves its k winners in keys_out, and the CTA that arrives
+// last at the counter (gridDim.x * k <= kSmallTile keys) runs the final rounds itself and zeroes the counter.
+template <typename Key, typename T>
+__global__ void __launch_bounds__(kRankThreads)
+topk_small_kernel(const T* __restrict__ values, const Key* __restrict__ keys_in, int n, int k, int worst,
+                  Key* __restrict__ keys_out, int32_t* __restrict__ idx_out, int* __restrict__ done) {
+    __shared__ Key wbest[kRankThreads / 32];
+    __shared__ Key winner;
+    __shared__ int last;
+    Key mine[kSmallItems];
+    const int base = blockIdx.x * kSmallTile;
+#pragma unroll
+    for (int i = 0; i < kSmallItems; ++i) {
+        const int g = base + i * kRankThreads + threadIdx.x;
+        mine[i] = Key::pad();
+        if (g < n) mine[i] = values ? Key::make(values[g], (uint32_t)g, worst != 0) : keys_in[g];
+    }
+    const bool partial = done != nullptr || idx_out == nullptr;
+    small_rounds(mine, k, worst, partial ? keys_out + (size_t)blockIdx.x * k : nullptr, partial ? nullptr : idx_out, wbest, &winner);
+    if (done == nullptr) return;
+    if (threadIdx.x == 0) {  // thread 0 wrote this CTA's winners
+        __threadfence();
+        last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int n2 = (int)gridDim.x * k;
+#pragma unroll
+    for (int i = 0; i < kSmallItems; ++i) {
+        const int g = i * kRankThreads + threadIdx.x;
+        mine[i] = g < n2 ? load_key_cg(keys_out + g) : Key::pad();
+    }
+    small_rounds(mine, k, worst, (Key*)nullptr, idx_out, wbest, &winner);
+    if (threadIdx.x == 0) *done = 0;
 }
 
 static int tile_for(int k) {
@@ -403,24 +440,31 @@ static int run_topk(const T* values, int P, int k, int worst, int32_t* idx, void
         auto small = topk_small_kernel<Key, T>;
         int nb = (P + kSmallTile - 1) / kSmallTile;
         if (nb == 1) {
-            small<<<1, kRankThreads, 0, st>>>(values, nullptr, P, k, worst, nullptr, idx);
+            small<<<1, kRankThreads, 0, st>>>(values, nullptr, P, k, worst, nullptr, idx, nullptr);
             TF_LAUNCH_CHECK();
             return TF_OK;
         }
         if (!ws || ws_bytes < workspace_bytes<Key>(P, k)) return TF_ERR_WORKSPACE;
         Key* a = reinterpret_cast<Key*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
         Key* b = a + (int64_t)nb * k;
-        small<<<nb, kRankThreads, 0, st>>>(values, nullptr, P, k, worst, a, nullptr);
+        if ((int64_t)nb * k <= kSmallTile) {  // one launch: the last CTA to finish merges the nb * k winners
+            int* done = sched_slot();
+            if (done == nullptr) return TF_ERR_NOMEM;
+            small<<<nb, kRankThreads, 0, st>>>(values, nullptr, P, k, worst, a, idx, done);
+            TF_LAUNCH_CHECK();
+            return TF_OK;
+        }
+        small<<<nb, kRankThreads, 0, st>>>(values, nullptr, P, k, worst, a, nullptr, nullptr);
         TF_LAUNCH_CHECK();
         int n = nb * k;
         while (true) {
             nb = (n + kSmallTile - 1) / kSmallTile;
             if (nb == 1) {
-                small<<<1, kRankThreads, 0, st>>>(nullptr, a, n, k, worst, nullptr, idx);
+                small<<<1, kRankThreads, 0, st>>>(nullptr, a, n, k, worst, nullptr, idx, nullptr);
                 TF_LAUNCH_CHECK();
                 return TF_OK;
             }
-            small<<<nb, kRankThreads, 0, st>>>(nullptr, a, n, k, worst, b, nullptr);
+            small<<<nb, kRankThreads, 0, st>>>(nullptr, a, n, k, worst, b, nullptr, nullptr);
             TF_LAUNCH_CHECK();
             n = nb * k;
             Key* t = a; a = b; b = t;
