@@ -195,35 +195,18 @@ struct SelState {
     unsigned long long prefix;  // digits chosen so far (high bits of K)
     int need;                   // rank of K inside the current prefix bucket (1-based)
     unsigned int count;         // compaction cursor
+    unsigned int done;          // CTAs that have added their histogram of the current pass
 };
 __host__ __device__ __forceinline__ int sel_shift(int pass) { return pass < 5 ? 53 - 11 * pass : 0; }
 __host__ __device__ __forceinline__ int sel_width(int pass) { return pass < 5 ? 11 : 9; }
 
 __global__ void sel_init_kernel(SelState* st, unsigned int* hist, int k) {
     for (int i = threadIdx.x; i < kSelPasses * kSelBins; i += blockDim.x) hist[i] = 0;
-    if (threadIdx.x == 0) { st->prefix = 0; st->need = k; st->count = 0; }
+    if (threadIdx.x == 0) { st->prefix = 0; st->need = k; st->count = 0; st->done = 0; }
 }
 
-__global__ void __launch_bounds__(256)
-sel_hist_kernel(const float* __restrict__ values, int P, int worst, int pass, const SelState* __restrict__ st,
-                unsigned int* __restrict__ hist) {
-    __shared__ unsigned int sh[kSelBins];
-    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    const int shift = sel_shift(pass), width = sel_width(pass);
-    const unsigned long long prefix = st->prefix;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
-        const unsigned long long key = Key32::make(values[i], (uint32_t)i, worst != 0).v;
-        const bool match = pass == 0 || (key >> (shift + width)) == prefix;
-        if (match) atomicAdd(&sh[(unsigned)(key >> shift) & ((1u << width) - 1u)], 1u);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x)
-        if (sh[i]) atomicAdd(&hist[pass * kSelBins + i], sh[i]);
-}
-
-// one block of 256 threads: pick the digit whose cumulative count reaches `need`
-__global__ void __launch_bounds__(256) sel_scan_kernel(int pass, SelState* st, const unsigned int* __restrict__ hist) {
+// one block of 256 threads (the last CTA of a histogram pass): pick the digit whose cumulative count reaches `need`
+__device__ __forceinline__ void sel_scan_block(int pass, SelState* st, const unsigned int* hist) {
     __shared__ unsigned int part[256];
     const unsigned int* h = hist + pass * kSelBins;
     const int nb = 1 << sel_width(pass);
@@ -233,7 +216,7 @@ __global__ void __launch_bounds__(256) sel_scan_kernel(int pass, SelState* st, c
 #pragma unroll
     for (int i = 0; i < per; ++i) {
         const int b = threadIdx.x * per + i;
-        loc[i] = b < nb ? h[b] : 0u;
+        loc[i] = b < nb ? __ldcg(h + b) : 0u;  // other CTAs' atomics: read through L2
         sum += loc[i];
     }
     part[threadIdx.x] = sum;
@@ -260,6 +243,33 @@ __global__ void __launch_bounds__(256) sel_scan_kernel(int pass, SelState* st, c
         st->need = (int)(need - run);
         st->prefix = (st->prefix << sel_width(pass)) | (unsigned long long)b;
     }
+}
+
+__global__ void __launch_bounds__(256)
+sel_hist_kernel(const float* __restrict__ values, int P, int worst, int pass, SelState* st, unsigned int* hist) {
+    __shared__ unsigned int sh[kSelBins];
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const int shift = sel_shift(pass), width = sel_width(pass);
+    const unsigned long long prefix = st->prefix;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+        const unsigned long long key = Key32::make(values[i], (uint32_t)i, worst != 0).v;
+        const bool match = pass == 0 || (key >> (shift + width)) == prefix;
+        if (match) atomicAdd(&sh[(unsigned)(key >> shift) & ((1u << width) - 1u)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[pass * kSelBins + i], sh[i]);
+    // the CTA that arrives last has the complete histogram in front of it: it picks the digit (no second launch)
+    __shared__ int last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(&st->done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    sel_scan_block(pass, st, hist);
+    if (threadIdx.x == 0) st->done = 0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -302,8 +312,6 @@ static int run_select(const float* values, int P, int k, int worst, int32_t* idx
     const int grid = min((P + 255) / 256, sm_count() * 8);
     for (int pass = 0; pass < kSelPasses; ++pass) {
         sel_hist_kernel<<<grid, 256, 0, st>>>(values, P, worst, pass, state, hist);
-        TF_LAUNCH_CHECK();
-        sel_scan_kernel<<<1, 256, 0, st>>>(pass, state, hist);
         TF_LAUNCH_CHECK();
     }
     sel_collect_kernel<<<grid, 256, 0, st>>>(values, P, worst, k, state, keys);
@@ -412,8 +420,6 @@ static int run_select_set(const float* values, int P, int k, int worst, int32_t*
     const int grid = min((P + 255) / 256, sm_count() * 8);
     for (int pass = 0; pass < kSelPasses; ++pass) {
         sel_hist_kernel<<<grid, 256, 0, st>>>(values, P, worst, pass, state, hist);
-        TF_LAUNCH_CHECK();
-        sel_scan_kernel<<<1, 256, 0, st>>>(pass, state, hist);
         TF_LAUNCH_CHECK();
     }
     const int nblocks = (P + kSetBlock - 1) / kSetBlock;
