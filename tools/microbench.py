@@ -54,6 +54,13 @@ def main():
     out["ga_step_unfused"] = timeit(torch, lambda: B.ga_step(pop, fit, top, ga, seed=1, generation=1, out=nxt, want_parity=False))
     ga2 = L.default_ga_params(selection=L.SEL_TRUNCATION, n_top=10)
     out["generation_fused_truncation"] = timeit(torch, lambda: B.generation(env, pop, fit, top, ga2, params, seed=1, generation=1, out_pop=nxt, out_fit=nfit))
+    # the same fused generation with no environment at all (segment arithmetic only): what the row traffic costs
+    empty = B.Environment.empty()
+    out["generation_fused_no_environment"] = timeit(torch, lambda: B.generation(empty, pop, fit, top, ga, params, seed=1, generation=1, out_pop=nxt, out_fit=nfit))
+    out["generation_fused_no_environment_truncation"] = timeit(torch, lambda: B.generation(empty, pop, fit, top, ga2, params, seed=1, generation=1, out_pop=nxt, out_fit=nfit))
+    out["fitness_no_environment"] = timeit(torch, lambda: B.fitness_batch(pop, None, empty, params, out=fit, want_collisions=False))
+    perm = torch.randperm(P, device="cuda")
+    out["gather_rows(torch.index_select, random permutation)"] = timeit(torch, lambda: torch.index_select(pop, 0, perm, out=nxt))
     src = torch.empty_like(pop)
     out["copy_pop_d2d(torch)"] = timeit(torch, lambda: src.copy_(pop))
     bytes_gen = (32 * W + 12) * P
