@@ -61,6 +61,8 @@ def main():
     out["fitness_no_environment"] = timeit(torch, lambda: B.fitness_batch(pop, None, empty, params, out=fit, want_collisions=False))
     perm = torch.randperm(P, device="cuda")
     out["gather_rows(torch.index_select, random permutation)"] = timeit(torch, lambda: torch.index_select(pop, 0, perm, out=nxt))
+    out["fill_pop(torch.zero_, write only)"] = timeit(torch, lambda: nxt.zero_())
+    out["sum_pop(torch.sum, read only)"] = timeit(torch, lambda: torch.sum(pop))
     src = torch.empty_like(pop)
     out["copy_pop_d2d(torch)"] = timeit(torch, lambda: src.copy_(pop))
     bytes_gen = (32 * W + 12) * P
