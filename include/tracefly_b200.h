@@ -99,7 +99,8 @@ int tf_env_static_index_stats(const tf_env* env, int64_t* n_lists, int64_t* n_ov
  * cells, one copy per band of `band` consecutive integer times, whose entries list (up to `cap`) the
  * spheres that can be nearest to, or collide with, a point of the cell at a time of the band
  * (t < time_slices).  Results are bit-identical to the brute-force loop; points outside the box,
- * fractional times and overflowed cells fall back to it. */
+ * fractional times and overflowed cells fall back to it — so make the box generous: a warp waits for
+ * its slowest lane, and one waypoint a few cells past the wall costs the whole warp the full loop. */
 int tf_env_build_dynamic_index(tf_env* env, int time_slices, int band, const float box_lo[3],
                                const float box_hi[3], float cell, int cap, void* stream);
 /* Diagnostics of the index: number of lists, overflowed lists, mean / max list length. */
