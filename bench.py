@@ -270,25 +270,26 @@ def run_gpu(args):
         torch.cuda.empty_cache()
 
         def run_e2e(fmt, steps):
-            stepper = B.HostStepper(env, P, W, ga, params, fmt=fmt, depth=2)
+            depth = int(os.environ.get("TF_E2E_DEPTH", 2))
+            stepper = B.HostStepper(env, P, W, ga, params, fmt=fmt, depth=depth)
             hdt, hc = B.HostStepper._HOST[fmt]
-            hosts = [torch.empty((P, W, hc), dtype=hdt).pin_memory() for _ in range(2)]
+            hosts = [torch.empty((P, W, hc), dtype=hdt).pin_memory() for _ in range(depth)]
             for h in hosts:
                 h.copy_(island.pop[..., :hc].to(hdt))
             sync_all()
             tickets = []
             checksum = 0.0
             t_start = None
-            for it in range(steps + 2):          # 2 untimed warm-up requests
-                if it == 2:
+            for it in range(steps + depth):      # `depth` untimed warm-up requests
+                if it == depth:
                     while tickets:
                         stepper.result(tickets.pop(0))
                     sync_all()
                     t_start = time.perf_counter()
-                if len(tickets) == 2:
+                if len(tickets) == depth:
                     fit_h, next_h = stepper.result(tickets.pop(0))
                     checksum += float(fit_h[0])      # the caller really reads the result
-                tickets.append(stepper.submit(hosts[it % 2], seed=SEED, generation=1000 + it))
+                tickets.append(stepper.submit(hosts[it % depth], seed=SEED, generation=1000 + it))
             while tickets:
                 fit_h, next_h = stepper.result(tickets.pop(0))
                 checksum += float(fit_h[0])
@@ -306,7 +307,7 @@ def run_gpu(args):
                     "host_format": {"f32": "float32[P,W,4] (the device layout)", "xyz": "float32[P,W,3] (the reference's 3-tuples as an array)",
                                     "i16": "int16[P,W,4] (lattice chromosomes)"}[fmt],
                     "what": "pinned host population in -> tf_fitness + tf_rank_topk + tf_generation -> host fitness "
-                            "vector + next population out; 2 requests in flight (D2H of step n overlaps H2D of step n+1); "
+                            f"vector + next population out; {depth} requests in flight (D2H of step n overlaps H2D of step n+1); "
                             "wall clock around the whole loop incl. the final drain"}
 
         e2e_steps = max(4, min(args.steps, 10))
