@@ -421,6 +421,7 @@ extern "C" int tf_env_build_dynamic_index(tf_env* env, int time_slices, int band
     if (time_slices < 1 || time_slices > 4096 || band < 1 || cell <= 0.0f || cap < 1 || cap > 1024) return TF_ERR_SHAPE;
     if (env->d.n_dyn > kIdxThreads * kIdxMaxPerThread) return TF_ERR_SHAPE;
     const int nbands = (time_slices + band - 1) / band;
+    cap = (cap + 3) & ~3;  // lists are read as int4
     int g[3];
     for (int a = 0; a < 3; ++a) {
         if (!(box_hi[a] > box_lo[a])) return TF_ERR_SHAPE;
@@ -446,6 +447,10 @@ extern "C" int tf_env_build_dynamic_index(tf_env* env, int time_slices, int band
     env->d.dcand = cand; env->d.dcount = count;
     env->d.dT = time_slices; env->d.dband = band; env->d.dgx = g[0]; env->d.dgy = g[1]; env->d.dgz = g[2]; env->d.dcap = cap;
     env->d.dox = box_lo[0]; env->d.doy = box_lo[1]; env->d.doz = box_lo[2]; env->d.dinv_h = 1.0f / cell;
+    uint32_t magic = (uint32_t)(((1u << 20) + (uint32_t)band - 1u) / (uint32_t)band);
+    for (int t = 0; t < time_slices && magic; ++t)
+        if ((((uint32_t)t * magic) >> 20) != (uint32_t)(t / band)) magic = 0;
+    env->d.dband_magic = magic;
     env->d.n_dyn_smem = 0;  // the kernels read the records through L1 / L2 now
     return TF_OK;
 }
@@ -562,6 +567,7 @@ extern "C" int tf_env_set_hazard(tf_env* env, const float* hazard_dev, int nt, i
     if (rc != TF_OK) return rc;
     // the env owns a transposed copy [y][x][t] (see hazard_sample); the caller's tensor is not kept
     const size_t n = (size_t)nt * ny * nx;
+    if (n >= ((size_t)1 << 31)) return TF_ERR_SHAPE;  // the kernels index the map with 32 bits
     TF_CUDA(cudaMalloc(&env->hazard_block, n * 4));
     hazard_transpose_kernel<<<(unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256>>>(
         hazard_dev, (float*)env->hazard_block, nt, (size_t)ny * nx);

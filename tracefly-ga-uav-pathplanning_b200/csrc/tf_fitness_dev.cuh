@@ -244,6 +244,11 @@ __device__ __forceinline__ void eval_dynamic(const EnvDev& e, const Tables& t, c
         }
         return;
     }
+    // Candidate lists.  The list walk is a chain of dependent loads (count -> ids -> records) that mostly hit
+    // L2 on a spread-out population, so the independent parts go first: all NP cells and counts, then the
+    // first four ids of every list (lists are 16-byte aligned: cap % 4 == 0), and ids are read four at a time.
+    int cnt[NP];
+    uint32_t cell[NP];
 #pragma unroll
     for (int s = 0; s < NP; ++s) {
         const int ti = (int)tm[s];
@@ -251,26 +256,37 @@ __device__ __forceinline__ void eval_dynamic(const EnvDev& e, const Tables& t, c
                   iz = __float2int_rd((z[s] - e.doz) * e.dinv_h);
         const bool indexed = (float)ti == tm[s] && ti >= 0 && ti < e.dT && (unsigned)ix < (unsigned)e.dgx &&
                              (unsigned)iy < (unsigned)e.dgy && (unsigned)iz < (unsigned)e.dgz;
-        int cnt = -1;
-        size_t cell = 0;
+        cnt[s] = -1;
+        cell[s] = 0;  // < 2^26 lists (tf_env_build_dynamic_index)
         if (indexed) {
-            cell = ((size_t)(ti / e.dband) * e.dgz + iz) * e.dgy * e.dgx + (size_t)iy * e.dgx + ix;
-            cnt = __ldg(e.dcount + cell);
+            const uint32_t tb = e.dband_magic ? ((uint32_t)ti * e.dband_magic) >> 20 : (uint32_t)(ti / e.dband);
+            cell[s] = ((tb * (uint32_t)e.dgz + (uint32_t)iz) * (uint32_t)e.dgy + (uint32_t)iy) * (uint32_t)e.dgx + (uint32_t)ix;
+            cnt[s] = __ldg(e.dcount + cell[s]);
         }
+    }
+    constexpr bool kAhead = NP <= 4;  // more slots than that would only spill the prefetched ids
+    int4 first[kAhead ? NP : 1];
+    if constexpr (kAhead) {
+#pragma unroll
+        for (int s = 0; s < NP; ++s)
+            if (cnt[s] > 0) first[s] = __ldg(reinterpret_cast<const int4*>(e.dcand + (size_t)cell[s] * (uint32_t)e.dcap));
+    }
+#pragma unroll
+    for (int s = 0; s < NP; ++s) {
         bool h = false;
-        if (cnt >= 0) {
-            const int32_t* list = e.dcand + cell * e.dcap;
-            int j = 0;
-            for (; j + 2 <= cnt; j += 2) {  // 2 ids, then 4 independent record loads in flight
-                const int i0 = __ldg(list + j), i1 = __ldg(list + j + 1);
-                const float4 a0 = __ldg(e.dynA + i0), a1 = __ldg(e.dynA + i1);
-                const float4 b0 = __ldg(e.dynB + i0), b1 = __ldg(e.dynB + i1);
-                dyn_test(a0, b0, x[s], y[s], z[s], tm[s], h, m2[s]);
-                dyn_test(a1, b1, x[s], y[s], z[s], tm[s], h, m2[s]);
-            }
-            for (; j < cnt; ++j) {
-                const int id = __ldg(list + j);
-                dyn_test(__ldg(e.dynA + id), __ldg(e.dynB + id), x[s], y[s], z[s], tm[s], h, m2[s]);
+        if (cnt[s] >= 0) {
+            const int4* list = reinterpret_cast<const int4*>(e.dcand + (size_t)cell[s] * (uint32_t)e.dcap);
+            const int n = cnt[s];
+            int4 q = make_int4(0, 0, 0, 0);
+            if (n > 0) q = kAhead ? first[kAhead ? s : 0] : __ldg(list);
+            for (int j = 0; j < n; j += 4) {
+                int4 nq = q;
+                if (j + 4 < n) nq = __ldg(list + (j >> 2) + 1);
+                dyn_test(__ldg(e.dynA + q.x), __ldg(e.dynB + q.x), x[s], y[s], z[s], tm[s], h, m2[s]);
+                if (j + 1 < n) dyn_test(__ldg(e.dynA + q.y), __ldg(e.dynB + q.y), x[s], y[s], z[s], tm[s], h, m2[s]);
+                if (j + 2 < n) dyn_test(__ldg(e.dynA + q.z), __ldg(e.dynB + q.z), x[s], y[s], z[s], tm[s], h, m2[s]);
+                if (j + 3 < n) dyn_test(__ldg(e.dynA + q.w), __ldg(e.dynB + q.w), x[s], y[s], z[s], tm[s], h, m2[s]);
+                q = nq;
             }
         } else {  // outside the index (or an overflowed cell): every sphere, from global memory
             for (int k = 0; k < e.n_dyn; ++k)
@@ -320,13 +336,12 @@ __device__ __forceinline__ float hazard_sample(const EnvDev& e, float x, float y
     int x1 = min(x0 + 1, e.hnx - 1), y1 = min(y0 + 1, e.hny - 1), t1 = min(t0 + 1, e.nt - 1);
     float fx = __fsub_rn(gx, (float)x0), fy = __fsub_rn(gy, (float)y0), ft = __fsub_rn(gt, (float)t0);
     // the env keeps the map transposed to [y][x][t]: the lanes of a warp are consecutive waypoints, i.e.
-    // nearly the same (x, y) at consecutive times, so their taps fall into the same cache lines
-    const float* c00 = e.hazard + ((size_t)y0 * e.hnx + x0) * e.nt;
-    const float* c01 = e.hazard + ((size_t)y0 * e.hnx + x1) * e.nt;
-    const float* c10 = e.hazard + ((size_t)y1 * e.hnx + x0) * e.nt;
-    const float* c11 = e.hazard + ((size_t)y1 * e.hnx + x1) * e.nt;
-    float v000 = __ldg(c00 + t0), v001 = __ldg(c01 + t0), v010 = __ldg(c10 + t0), v011 = __ldg(c11 + t0);
-    float v100 = __ldg(c00 + t1), v101 = __ldg(c01 + t1), v110 = __ldg(c10 + t1), v111 = __ldg(c11 + t1);
+    // nearly the same (x, y) at consecutive times, so their taps fall into the same cache lines.
+    // 32-bit element indices (the map has < 2^31 elements): one 64-bit address, small offsets for the taps
+    const float* c00 = e.hazard + (uint32_t)((y0 * e.hnx + x0) * e.nt + t0);
+    const int ox = (x1 - x0) * e.nt, oy = (y1 - y0) * e.hnx * e.nt, ot = t1 - t0;
+    float v000 = __ldg(c00), v001 = __ldg(c00 + ox), v010 = __ldg(c00 + oy), v011 = __ldg(c00 + oy + ox);
+    float v100 = __ldg(c00 + ot), v101 = __ldg(c00 + ox + ot), v110 = __ldg(c00 + oy + ot), v111 = __ldg(c00 + oy + ox + ot);
     float a0 = lerp_f(lerp_f(v000, v001, fx), lerp_f(v010, v011, fx), fy);
     float a1 = lerp_f(lerp_f(v100, v101, fx), lerp_f(v110, v111, fx), fy);
     return lerp_f(a0, a1, ft);
