@@ -217,6 +217,10 @@ def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind, P):
         env.set_hazard(torch.from_numpy(rng.uniform(0, 1, size=(8, 16, 16)).astype(np.float32)).cuda(), 0.25, 0.25, 0, 0, 7.0 / (W - 1))
     prm = L.default_params(hazard_weight=0.3)
     pop = B.init_walks(5, P, W, start=(32, 32, 32), lo=(0, 0, 0), hi=(63, 63, 63))
+    if P == 5003:   # off-lattice waypoints (what MAIN passes): fractional coordinates through the same kernels
+        g = torch.Generator(device="cuda")
+        g.manual_seed(W)
+        pop[..., :3] += torch.rand(pop[..., :3].shape, device="cuda", generator=g) * 0.75 - 0.25
     ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=3, mutation_rate=0.5, n_elite=3)
     res = []
     for disable, schedule in ((0, 0), (0, 1), (0, 2), (1, 0)):
