@@ -20,6 +20,7 @@ logic runs on CPU tensors under gloo in the tests (with the oracle's ops) — th
 uses `CudaOps`.
 """
 import contextlib
+import os
 
 import torch
 import torch.distributed as dist
@@ -38,7 +39,7 @@ class CudaOps:
         self.topk_elite = B.TopK(P, E) if E else None
         self.worst_set = B.SelectSet(P, n_worst) if n_worst else None
         self.side = torch.cuda.Stream() if n_worst else None
-        self.reserve_sms = 8
+        self.reserve_sms = int(os.environ.get("TRACEFLY_RESERVE_SMS", 8))
 
     def fitness(self, pop):
         return self.B.fitness_batch(pop, None, self.env, self.params, want_collisions=False)[0]
