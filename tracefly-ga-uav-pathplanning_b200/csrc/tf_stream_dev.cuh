@@ -530,14 +530,18 @@ static int launch_stream(const StreamArgs& a) {
         occ_smem = smem;
     }
     const int resident_warps = sm_count() * max(occ, 1) * kWarpsPerBlock;
-    // long runs (>= 4 tiles per resident warp): persistent grid, tickets from a global counter, and the
-    // population ends in half-size tiles, two per resident warp; short runs: static assignment
+    // long runs (>= 4 tiles per resident warp): persistent grid, tickets from a global counter.  The plain fused
+    // generation runs entirely on half-size tiles (16 children; measured at cfg3: tiles of 32 0.387 ms, 32 with
+    // a tail of 2 / 4 / 8 half-size tiles per resident warp 0.385 / 0.378 / 0.377 ms, all 16 0.374 ms, all 8
+    // 0.391 ms); the fitness sweeps and the hazard / moving-sphere variants keep tiles of 32 and end in two
+    // half-size tiles per resident warp (all-16 there: fitness sweep without environment 0.192 -> 0.252 ms,
+    // cfg4 1.17 -> 1.23 ms).  Short runs: static assignment.
     int n_big = (a.P + T - 1) / T, n_small = 0;
     int* sched = nullptr;
     int grid = min((n_big + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
     if (T >= 8 && a.P / T >= 4 * resident_warps) {
         const int Ts = T >> 1;
-        n_big = (a.P - 2 * resident_warps * Ts) / T;
+        n_big = (GA && XF == 0) ? 0 : (a.P - 2 * resident_warps * Ts) / T;
         n_small = (a.P - n_big * T + Ts - 1) / Ts;
         sched = sched_slot();
         if (sched == nullptr) return TF_ERR_NOMEM;
