@@ -118,3 +118,12 @@ def test_cfg3_full_size(tf):
     assert torch.equal(nxt[:2], pop[top[:2].long()])
     refit, _ = B.fitness_batch(nxt, None, env, params)
     assert torch.equal(refit, nfit)                                  # the fused sweep scored what it wrote
+    # the whole next population (1M x 64: selection, crossover points, mutations, elites) vs the CPU restatement
+    oga = O.default_ga(selection=ga.selection, tournament_k=ga.tournament_k, crossover=ga.crossover, mutation=ga.mutation,
+                       mutation_rate=ga.mutation_rate, n_elite=ga.n_elite, stream_id=ga.stream_id)
+    O.set_threads(16)
+    onxt, _, osel, ocp = O.ga_step(pop.cpu().numpy(), fit.cpu().numpy(), top.cpu().numpy(), oga, seed=5, gen=2)
+    O.set_threads(1)
+    assert np.array_equal(onxt, nxt.cpu().numpy())
+    _, _, _, sel, cp = B.generation(env, pop, fit, top, ga, params, seed=5, generation=2, want_parity=True)
+    assert np.array_equal(osel, sel.cpu().numpy()) and np.array_equal(ocp, cp.cpu().numpy())
