@@ -1,5 +1,5 @@
 """Parity at BASELINE.json's full sizes (configs[1]: 65,536 x 32 vs 1,024 analytic obstacles; configs[2]:
-1,048,576 x 64 vs a 1024^3 voxel grid).  The CPU oracle cannot sweep these in seconds, so the checks
+1,048,576 x 64 vs a 1024^3 voxel grid; configs[3]: the same + hazard map + 1,024 moving spheres).  The CPU oracle cannot sweep these in seconds, so the checks
 are (a) the oracle on a seeded sample of the same launch, and (b) size-independent properties:
 batch independence, permutation equivariance, voxel flags == analytic flags, TMA path == LSU path,
 fused == unfused, elites carried over, children are splices of the recorded parents, stable top-k."""
@@ -127,3 +127,36 @@ def test_cfg3_full_size(tf):
     assert np.array_equal(onxt, nxt.cpu().numpy())
     _, _, _, sel, cp = B.generation(env, pop, fit, top, ga, params, seed=5, generation=2, want_parity=True)
     assert np.array_equal(osel, sel.cpu().numpy()) and np.array_equal(ocp, cp.cpu().numpy())
+
+
+def test_cfg4_full_size(tf):
+    """configs[3]: cfg3 + hazard map + 1,024 moving spheres (candidate index with a margin).  The oracle on a
+    seeded sample of the full launch, index == brute force, and the fused generation scores what it writes —
+    on a population evolved until waypoints have drifted past the world box."""
+    torch, L, B = tf
+    cfg = dict(bench.WORKLOADS["cfg4"])
+    P, W = cfg["P"], cfg["W"]
+    env, params, pop, ga = bench.build_gpu_workload(cfg, 0, torch, B, L)
+    fit, coll = B.fitness_batch(pop, None, env, params)
+    top = B.rank_topk(fit, 2)
+    for g in range(12):                                               # let mutations push waypoints around
+        pop, fit, *_ = B.generation(env, pop, fit, top, ga, params, seed=bench.SEED, generation=g)
+        top = B.rank_topk(fit, 2)
+    fit, coll = B.fitness_batch(pop, None, env, params)
+    nxt, nfit, *_ = B.generation(env, pop, fit, top, ga, params, seed=5, generation=99)
+    refit, _ = B.fitness_batch(nxt, None, env, params)
+    assert torch.equal(refit, nfit)
+    # oracle (brute force over the spheres, its own hazard sampler) on a sample that includes out-of-box chromosomes
+    wx, wy, wz = cfg["world"]
+    outside = ((pop[..., :3] < 0) | (pop[..., :3] >= torch.tensor([wx, wy, wz], device="cuda"))).any(-1).any(-1)
+    idx = np.random.default_rng(4).choice(P, 2048, replace=False)
+    idx = np.unique(np.concatenate([idx, torch.nonzero(outside).flatten()[:512].cpu().numpy()]))
+    table = bench.obstacle_table(cfg, cfg["n_voxel_obs"], 10, bench.SEED + 2)
+    venv = O.OracleEnv(O.SEM_PF, O.obstacle_table(table[:, :3], table[:, 3], table[:, 7].astype(np.int32)), 0.0)
+    bricks_h = O.voxelize(venv, *cfg["world"])
+    oenv = O.OracleEnv(O.SEM_NONE, None, 0.0, bricks=bricks_h, dims=cfg["world"], dyn=bench.dyn_table(cfg, cfg["n_dyn"], bench.SEED),
+                       dyn_safety=2.0, hazard=bench.hazard_field(), hazard_map=(0.25, 0.25, 0.0, 0.0, 23.0 / (W - 1)))
+    O.set_threads(16)
+    ofit, ocoll = O.fitness_f32(oenv, pop[idx].cpu().numpy(), None, O.default_params(guard=1, hazard_weight=0.5))
+    O.set_threads(1)
+    assert np.array_equal(ofit, fit[idx].cpu().numpy()) and np.array_equal(ocoll, as_u32(coll[idx]))
