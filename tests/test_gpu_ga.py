@@ -194,11 +194,12 @@ def test_init_populations(tf):
 
 
 @pytest.mark.parametrize("P", [5003, 230003, 700001])   # tiles of 4 / of 32 (static) / dynamic tickets; ragged
-@pytest.mark.parametrize("W", [32, 64])
-@pytest.mark.parametrize("env_kind", ["none", "pf", "vox+dyn+haz"])
+@pytest.mark.parametrize("W", [3, 20, 32, 48, 63, 64])
+@pytest.mark.parametrize("env_kind", ["none", "pf", "vox+dyn+haz", "vox+dyn+haz, no table"])
 def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind, P):
-    """The TMA-staged kernels (W = 32/64), in both schedules (one chromosome per warp step / two), must give
-    bit-identical results to the LSU-path kernels."""
+    """The TMA-staged kernels (W = 32 / 64 everywhere; any W <= 64 with masked lanes where there is no obstacle
+    table), in both schedules (one chromosome per warp step / two), must give bit-identical results to the
+    LSU-path kernels."""
     torch, L, B = tf
     rng = np.random.default_rng(W)
     dims = (64, 64, 64)
@@ -208,7 +209,8 @@ def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind, P):
     elif env_kind == "pf":
         env = B.Environment(L.SEM_PF, table, 0.0)
     else:
-        env = B.Environment(L.SEM_HR, table[:40], 2.0).set_voxels(B.voxelize(table, dims, L.SEM_PF), dims)
+        env = B.Environment(L.SEM_HR, table[:40], 2.0) if env_kind == "vox+dyn+haz" else B.Environment.empty()
+        env.set_voxels(B.voxelize(table, dims, L.SEM_PF), dims)
         dyn = np.zeros((16, 8), np.float32)
         dyn[:, :3] = rng.uniform(0, 64, size=(16, 3))
         dyn[:, 3] = 2

@@ -269,15 +269,19 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 // children j and T/2 + j = lanes j and 16 + j, so every total ends in the half where its owner sits.
 // XF 1 (hazard map / moving spheres): 2 CTAs / SM = up to 128 registers; at 3 (80 registers) the candidate-list
 // loop spilled 250 bytes and cfg4 ran 8 % slower
-template <int NW, int SEM, bool VOX, int XF, bool GA>
+// RAGW: the row length is a runtime value Wr <= 32 NW (any chromosome length up to 64 on the TMA-staged path);
+// lanes whose waypoint index is >= Wr are masked.  RAGW = false: W = 32 NW, the code of the BASELINE configs.
+template <int NW, int SEM, bool VOX, int XF, bool GA, bool RAGW>
 __global__ void __launch_bounds__(kBlockThreads, (XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? 2 : 0))
 duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
            const __grid_constant__ tf_ga_params ga, const float4* __restrict__ pop,
            const float* __restrict__ fit, const int32_t* __restrict__ top_idx,
            const tf_draw* __restrict__ tape, uint64_t seed, uint32_t gen, int P, int T,
            float4* __restrict__ next, float* __restrict__ out_fit, uint32_t* __restrict__ out_coll,
-           int32_t* __restrict__ sel, int32_t* __restrict__ cpo, int n_big, int n_tickets, int* __restrict__ sched) {
-    constexpr int W = 32 * NW, NL = 2 * NW, kPairStages = kStages / 2;
+           int32_t* __restrict__ sel, int32_t* __restrict__ cpo, int n_big, int n_tickets, int* __restrict__ sched,
+           int Wr) {
+    constexpr int NL = 2 * NW, kPairStages = kStages / 2;
+    const int W = RAGW ? Wr : 32 * NW;
     extern __shared__ __align__(128) unsigned char smem_stream[];
     unsigned char* smem = smem_stream;
     const SmemLayout sm = carve_smem(e, smem);
@@ -393,12 +397,13 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
 #pragma unroll
             for (int m = 0; m < NL; ++m) {
                 const int k = h + 16 * m;
-                const float4 v = row[k];
-                const float4 q = row[k > 0 ? k - 1 : 0];
+                const bool ok = !RAGW || k < W;   // masked lanes sit at (-1, -1, -1): outside every grid
+                const float4 v = ok ? row[k] : make_float4(-1.0f, -1.0f, -1.0f, 0.0f);
+                const float4 q = ok ? row[k > 0 ? k - 1 : 0] : v;
                 cur.x[m] = v.x; cur.y[m] = v.y; cur.z[m] = v.z;
                 prev.x[m] = q.x; prev.y[m] = q.y; prev.z[m] = q.z;
                 if constexpr (GA) {
-                    if (live) stg_stream_hint(dst + k, v, pol_stream);
+                    if (live && ok) stg_stream_hint(dst + k, v, pol_stream);
                 }
             }
             VoxRegs<NL> vr;
@@ -430,6 +435,7 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
 #pragma unroll
             for (int m = 0; m < NL; ++m) {
                 const int k = h + 16 * m, v = m & 1;
+                if (RAGW && k >= W) continue;
                 if (has_dist) a_prox[v] = __fadd_rn(a_prox[v], __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[m])));  // HR:46
                 if constexpr (XF >= 1) {
                     if (e.hazard != nullptr) a_haz[v] = __fadd_rn(a_haz[v], hazard_sample(e, cur.x[m], cur.y[m], (float)k));
@@ -439,13 +445,14 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
                     const float dx = cur.x[m] - px, dy = cur.y[m] - py, dz = cur.z[m] - pz;
                     a_dist[v] = __fadd_rn(a_dist[v], sqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
                     a_alt[v] = __fadd_rn(a_alt[v], fabsf(dz));                      // HR:44
-                    if (m < NL - 1 || h < 15) turns += (cur.x[m] != px || cur.y[m] != py) ? 1 : 0;  // k <= W-2, HR:38-40,43
+                    if (RAGW ? k <= W - 2 : (m < NL - 1 || h < 15)) turns += (cur.x[m] != px || cur.y[m] != py) ? 1 : 0;  // k <= W-2, HR:38-40,43
                 }
             }
 #pragma unroll
             for (int m = 0; m < NL; ++m) {
                 bool hm = (hit >> m) & 1u;
                 if constexpr (VOX) hm = hm || (vr.word[m] & vr.mask[m]) != 0u;
+                if (RAGW) hm = hm && h + 16 * m < W;
                 cwords[m] = __ballot_sync(0xffffffffu, hm);
                 ncoll += hm ? 1 : 0;
             }
@@ -500,26 +507,9 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
     }
 }
 
-template <int NW, int SEM, bool VOX, int XF, bool GA>
-static int launch_stream(const StreamArgs& a) {
-    const size_t smem = stream_smem_bytes(*a.e, a.W);
-    const int T = tile_size_for(a.P);
-    // schedule: two chromosomes per warp step wherever there is no obstacle-table loop (measured faster on the
-    // voxel / hazard / moving-sphere variants); with a table loop the extra registers (104 vs 64) halve the
-    // occupancy and one chromosome per warp step stays ahead (cfg2: 56 us vs 71 us)
-    const bool duo = g_stream_schedule == 0 ? SEM == TF_SEM_NONE : g_stream_schedule == 2;
-    if (!duo) {  // one chromosome per warp step, static tile assignment
-        auto kern = stream_kernel<NW, SEM, VOX, XF, GA>;
-        if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int ntiles = (a.P + T - 1) / T;
-        const int grid = min((ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
-        kern<<<grid, kBlockThreads, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
-                                                  a.top_idx, a.tape, a.seed, a.gen, a.P, T,
-                                                  reinterpret_cast<float4*>(a.next), a.out_fit, a.out_coll, a.sel, a.cpo);
-        TF_LAUNCH_CHECK();
-        return TF_OK;
-    }
-    auto kern = duo_kernel<NW, SEM, VOX, XF, GA>;
+template <int NW, int SEM, bool VOX, int XF, bool GA, bool RAGW>
+static int launch_duo(const StreamArgs& a, size_t smem, int T) {
+    auto kern = duo_kernel<NW, SEM, VOX, XF, GA, RAGW>;
     if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static size_t occ_smem = ~(size_t)0;  // resident CTAs per SM of this variant with this much shared memory
     static int occ_cached = 0;
@@ -552,9 +542,35 @@ static int launch_stream(const StreamArgs& a) {
     kern<<<grid, kBlockThreads, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
                                               a.top_idx, a.tape, a.seed, a.gen, a.P, T,
                                               reinterpret_cast<float4*>(a.next), a.out_fit, a.out_coll, a.sel, a.cpo,
-                                              n_big, n_big + n_small, sched);
+                                              n_big, n_big + n_small, sched, a.W);
     TF_LAUNCH_CHECK();
     return TF_OK;
+}
+
+template <int NW, int SEM, bool VOX, int XF, bool GA>
+static int launch_stream(const StreamArgs& a) {
+    const size_t smem = stream_smem_bytes(*a.e, a.W);
+    const int T = tile_size_for(a.P);
+    // schedule: two chromosomes per warp step wherever there is no obstacle-table loop (measured faster on the
+    // voxel / hazard / moving-sphere variants); with a table loop the extra registers (104 vs 64) halve the
+    // occupancy and one chromosome per warp step stays ahead (cfg2: 56 us vs 71 us)
+    const bool duo = g_stream_schedule == 0 ? SEM == TF_SEM_NONE : g_stream_schedule == 2;
+    if (!duo) {  // one chromosome per warp step, static tile assignment
+        auto kern = stream_kernel<NW, SEM, VOX, XF, GA>;
+        if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int ntiles = (a.P + T - 1) / T;
+        const int grid = min((ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
+        kern<<<grid, kBlockThreads, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
+                                                  a.top_idx, a.tape, a.seed, a.gen, a.P, T,
+                                                  reinterpret_cast<float4*>(a.next), a.out_fit, a.out_coll, a.sel, a.cpo);
+        TF_LAUNCH_CHECK();
+        return TF_OK;
+    }
+    if (a.W != 32 * NW) {
+        if constexpr (SEM == TF_SEM_NONE) return launch_duo<NW, SEM, VOX, XF, GA, true>(a, smem, T);
+        else return TF_ERR_UNSUPPORTED;  // stream_eligible() never sends these here
+    }
+    return launch_duo<NW, SEM, VOX, XF, GA, false>(a, smem, T);
 }
 template <int NW, int SEM, bool GA>
 static int stream_flags(const StreamArgs& a) {
