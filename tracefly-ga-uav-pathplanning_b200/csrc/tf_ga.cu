@@ -75,7 +75,8 @@ int generation_lsu_nw4(const GenArgs&);
 int generation_lsu_nw8(const GenArgs&);
 int generation_stream_nw1(const StreamArgs&);
 int generation_stream_nw2(const StreamArgs&);
-static int generation_stream(const StreamArgs& a) { return a.W <= 32 ? generation_stream_nw1(a) : generation_stream_nw2(a); }
+int generation_stream_nw4(const StreamArgs&);
+static int generation_stream(const StreamArgs& a) { return a.W <= 32 ? generation_stream_nw1(a) : (a.W <= 64 ? generation_stream_nw2(a) : generation_stream_nw4(a)); }
 
 // ------------------------------------------------------------------------------------------
 template <typename V4, typename F>

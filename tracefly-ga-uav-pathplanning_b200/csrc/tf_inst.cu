@@ -23,11 +23,19 @@ int TF_CAT(generation_lsu_nw, TF_INST_NW)(const GenArgs& a) { return gen_sem<TF_
 #elif TF_INST_KIND == 2
 #include "tf_stream_dev.cuh"
 namespace tf {
+#if TF_INST_NW >= 4
+int TF_CAT(fitness_stream_nw, TF_INST_NW)(const StreamArgs& a) { return stream_long_rows<TF_INST_NW, false>(a); }
+#else
 int TF_CAT(fitness_stream_nw, TF_INST_NW)(const StreamArgs& a) { return stream_sem<TF_INST_NW, false>(a); }
+#endif
 }  // namespace tf
 #elif TF_INST_KIND == 3
 #include "tf_stream_dev.cuh"
 namespace tf {
+#if TF_INST_NW >= 4
+int TF_CAT(generation_stream_nw, TF_INST_NW)(const StreamArgs& a) { return stream_long_rows<TF_INST_NW, true>(a); }
+#else
 int TF_CAT(generation_stream_nw, TF_INST_NW)(const StreamArgs& a) { return stream_sem<TF_INST_NW, true>(a); }
+#endif
 }  // namespace tf
 #endif

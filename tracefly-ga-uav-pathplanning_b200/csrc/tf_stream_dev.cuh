@@ -272,7 +272,7 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 // RAGW: the row length is a runtime value Wr <= 32 NW (any chromosome length up to 64 on the TMA-staged path);
 // lanes whose waypoint index is >= Wr are masked.  RAGW = false: W = 32 NW, the code of the BASELINE configs.
 template <int NW, int SEM, bool VOX, int XF, bool GA, bool RAGW>
-__global__ void __launch_bounds__(kBlockThreads, (XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? 2 : 0))
+__global__ void __launch_bounds__(kBlockThreads, NW >= 4 ? 2 : ((XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? 2 : 0)))
 duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
            const __grid_constant__ tf_ga_params ga, const float4* __restrict__ pop,
            const float* __restrict__ fit, const int32_t* __restrict__ top_idx,
@@ -579,6 +579,21 @@ static int stream_flags(const StreamArgs& a) {
     const bool xf1 = a.e->n_dyn > 0 || a.e->hazard != nullptr;
     if (vox) return xf1 ? launch_stream<NW, SEM, true, 1, GA>(a) : launch_stream<NW, SEM, true, 0, GA>(a);
     return xf1 ? launch_stream<NW, SEM, false, 1, GA>(a) : launch_stream<NW, SEM, false, 0, GA>(a);
+}
+// 64 < W <= 128 (NW = 4): only the two-chromosome kernel without an obstacle table is built (8 waypoints per
+// lane; the ring is 12 KB per warp, so 2 CTAs / SM and up to 128 registers)
+template <int NW, bool GA>
+static int stream_long_rows(const StreamArgs& a) {
+    const size_t smem = stream_smem_bytes(*a.e, a.W);
+    const int T = tile_size_for(a.P);
+    const bool vox = a.e->bricks != nullptr;
+    const bool xf1 = a.e->n_dyn > 0 || a.e->hazard != nullptr;
+    if (a.W == 32 * NW) {
+        if (vox) return xf1 ? launch_duo<NW, TF_SEM_NONE, true, 1, GA, false>(a, smem, T) : launch_duo<NW, TF_SEM_NONE, true, 0, GA, false>(a, smem, T);
+        return xf1 ? launch_duo<NW, TF_SEM_NONE, false, 1, GA, false>(a, smem, T) : launch_duo<NW, TF_SEM_NONE, false, 0, GA, false>(a, smem, T);
+    }
+    if (vox) return xf1 ? launch_duo<NW, TF_SEM_NONE, true, 1, GA, true>(a, smem, T) : launch_duo<NW, TF_SEM_NONE, true, 0, GA, true>(a, smem, T);
+    return xf1 ? launch_duo<NW, TF_SEM_NONE, false, 1, GA, true>(a, smem, T) : launch_duo<NW, TF_SEM_NONE, false, 0, GA, true>(a, smem, T);
 }
 template <int NW, bool GA>
 static int stream_sem(const StreamArgs& a) {
