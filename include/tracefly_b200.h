@@ -317,7 +317,7 @@ void tf_philox4x32_10(uint32_t key0, uint32_t key1, uint32_t c0, uint32_t c1, ui
  * whose result differs from sqrt.rn.f32.  count <= 2^32. */
 int tf_selftest_sqrt(uint32_t first_bits, uint64_t count, uint64_t* mismatches_dev, void* stream);
 /* Options.  TF_OPT_DISABLE_STREAM = 1 forces the LSU-path kernels even where the TMA-staged
- * kernels apply (fixed length W <= 64; with an obstacle table W = 32 / 64); both give bit-identical results. */
+ * kernels apply (fixed length W <= 256; with an obstacle table W = 32 / 64); both give bit-identical results. */
 #define TF_OPT_DISABLE_STREAM 1
 /* TF_OPT_STREAM_SCHEDULE: how the TMA-staged kernels walk a tile.  1 = one chromosome per warp step,
  * 2 = two (one per half-warp, dynamic tile tickets), 0 (default) = the library picks per kernel variant.

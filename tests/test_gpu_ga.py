@@ -194,10 +194,10 @@ def test_init_populations(tf):
 
 
 @pytest.mark.parametrize("P", [5003, 230003, 700001])   # tiles of 4 / of 32 (static) / dynamic tickets; ragged
-@pytest.mark.parametrize("W", [3, 20, 32, 48, 63, 64, 100, 128])
+@pytest.mark.parametrize("W", [3, 20, 32, 48, 63, 64, 70, 100, 128, 200, 256])
 @pytest.mark.parametrize("env_kind", ["none", "pf", "vox+dyn+haz", "vox+dyn+haz, no table"])
 def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind, P):
-    """The TMA-staged kernels (W = 32 / 64 everywhere; any W <= 128 with masked lanes where there is no obstacle
+    """The TMA-staged kernels (W = 32 / 64 everywhere; any W <= 256 with masked lanes where there is no obstacle
     table), in both schedules (one chromosome per warp step / two), must give bit-identical results to the
     LSU-path kernels."""
     torch, L, B = tf

@@ -42,7 +42,7 @@ def _stale():
 
 # tf_inst.cu is compiled once per (kernel family, waypoints-per-lane): the template instantiations
 # (hundreds of kernels) then build in parallel instead of inside two giant translation units.
-INSTANCES = [(kind, nw) for kind in (0, 1) for nw in (1, 2, 4, 8)] + [(kind, nw) for kind in (2, 3) for nw in (1, 2, 4)]
+INSTANCES = [(kind, nw) for kind in (0, 1) for nw in (1, 2, 4, 8)] + [(kind, nw) for kind in (2, 3) for nw in (1, 2, 4, 8)]
 MAX_JOBS = max(1, min(8, os.cpu_count() or 1))
 
 

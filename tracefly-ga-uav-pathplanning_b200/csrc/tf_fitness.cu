@@ -13,7 +13,8 @@ int fitness_lsu_nw8(const EnvDev&, const tf_params&, const float*, const int32_t
 int fitness_stream_nw1(const StreamArgs&);
 int fitness_stream_nw2(const StreamArgs&);
 int fitness_stream_nw4(const StreamArgs&);
-static int fitness_stream(const StreamArgs& a) { return a.W <= 32 ? fitness_stream_nw1(a) : (a.W <= 64 ? fitness_stream_nw2(a) : fitness_stream_nw4(a)); }
+int fitness_stream_nw8(const StreamArgs&);
+static int fitness_stream(const StreamArgs& a) { return a.W <= 32 ? fitness_stream_nw1(a) : (a.W <= 64 ? fitness_stream_nw2(a) : (a.W <= 128 ? fitness_stream_nw4(a) : fitness_stream_nw8(a))); }
 
 int check_fitness_args(const tf_env* env, const void* pop, int P, int W, const tf_params* prm, const void* fit) {
     if (!env || !pop || !prm || !fit) return TF_ERR_INVALID;

@@ -76,7 +76,8 @@ int generation_lsu_nw8(const GenArgs&);
 int generation_stream_nw1(const StreamArgs&);
 int generation_stream_nw2(const StreamArgs&);
 int generation_stream_nw4(const StreamArgs&);
-static int generation_stream(const StreamArgs& a) { return a.W <= 32 ? generation_stream_nw1(a) : (a.W <= 64 ? generation_stream_nw2(a) : generation_stream_nw4(a)); }
+int generation_stream_nw8(const StreamArgs&);
+static int generation_stream(const StreamArgs& a) { return a.W <= 32 ? generation_stream_nw1(a) : (a.W <= 64 ? generation_stream_nw2(a) : (a.W <= 128 ? generation_stream_nw4(a) : generation_stream_nw8(a))); }
 
 // ------------------------------------------------------------------------------------------
 template <typename V4, typename F>

@@ -272,7 +272,7 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 // RAGW: the row length is a runtime value Wr <= 32 NW (any chromosome length up to 64 on the TMA-staged path);
 // lanes whose waypoint index is >= Wr are masked.  RAGW = false: W = 32 NW, the code of the BASELINE configs.
 template <int NW, int SEM, bool VOX, int XF, bool GA, bool RAGW>
-__global__ void __launch_bounds__(kBlockThreads, NW >= 4 ? 2 : ((XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? 2 : 0)))
+__global__ void __launch_bounds__(kBlockThreads, NW >= 8 ? 1 : NW >= 4 ? 2 : ((XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? 2 : 0)))
 duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
            const __grid_constant__ tf_ga_params ga, const float4* __restrict__ pop,
            const float* __restrict__ fit, const int32_t* __restrict__ top_idx,
@@ -464,11 +464,21 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
                 return r;
             };
             const float dist = half_sum(a_dist), alt = half_sum(a_alt);
-            const uint32_t both = __reduce_add_sync(0xffffffffu, (uint32_t)(turns | (ncoll << 7)) << (half * 16));
+            // integer totals of both halves in one reduction: 16 bits per half (7 + 9 bits up to W = 128; longer
+            // rows take one reduction per count)
+            uint32_t turns_tot, ncoll_tot;
+            if constexpr (NW <= 4) {
+                const uint32_t both = __reduce_add_sync(0xffffffffu, (uint32_t)(turns | (ncoll << 7)) << (half * 16));
+                const uint32_t t16 = (both >> (half * 16)) & 0xffffu;
+                turns_tot = t16 & 127u;
+                ncoll_tot = t16 >> 7;
+            } else {
+                turns_tot = (__reduce_add_sync(0xffffffffu, (uint32_t)turns << (half * 16)) >> (half * 16)) & 0xffffu;
+                ncoll_tot = (__reduce_add_sync(0xffffffffu, (uint32_t)ncoll << (half * 16)) >> (half * 16)) & 0xffffu;
+            }
             if (h == j) {
-                const uint32_t t14 = (both >> (half * 16)) & 0xffffu;
                 sums.dist = dist; sums.alt = alt;
-                sums.packed = (int)((t14 & 127u) | ((t14 >> 7) << 10));
+                sums.packed = (int)(turns_tot | (ncoll_tot << 10));
 #pragma unroll
                 for (int w = 0; w < NW; ++w)
                     sums.cw[w] = __byte_perm(cwords[2 * w], cwords[2 * w + 1], half ? 0x7632 : 0x5410);
@@ -492,8 +502,10 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
             const int slot = slot0 + myc;
             out_fit[slot] = combine_fitness<NW, XF>(e, prm, sums);
             if (out_coll) {
+                const int nwords = RAGW ? (W + 31) >> 5 : NW;   // the flag array is [P][ceil(W / 32)]
 #pragma unroll
-                for (int s = 0; s < NW; ++s) out_coll[(size_t)slot * NW + s] = sums.cw[s];
+                for (int s = 0; s < NW; ++s)
+                    if (s < nwords) out_coll[(size_t)slot * nwords + s] = sums.cw[s];
             }
         }
         ticket = dynamic ? __shfl_sync(0xffffffffu, ahead, 0) : ahead;
@@ -580,8 +592,8 @@ static int stream_flags(const StreamArgs& a) {
     if (vox) return xf1 ? launch_stream<NW, SEM, true, 1, GA>(a) : launch_stream<NW, SEM, true, 0, GA>(a);
     return xf1 ? launch_stream<NW, SEM, false, 1, GA>(a) : launch_stream<NW, SEM, false, 0, GA>(a);
 }
-// 64 < W <= 128 (NW = 4): only the two-chromosome kernel without an obstacle table is built (8 waypoints per
-// lane; the ring is 12 KB per warp, so 2 CTAs / SM and up to 128 registers)
+// 64 < W <= 256 (NW = 4, 8): only the two-chromosome kernel without an obstacle table is built (8 / 16
+// waypoints per lane; the ring is 12 / 24 KB per warp, so 2 CTAs / SM and 128 registers, or 1 and 255)
 template <int NW, bool GA>
 static int stream_long_rows(const StreamArgs& a) {
     const size_t smem = stream_smem_bytes(*a.e, a.W);

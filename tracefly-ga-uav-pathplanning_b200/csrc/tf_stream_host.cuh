@@ -30,7 +30,7 @@ inline bool stream_eligible(const EnvDev& e, const tf_params& prm, int W, bool u
     if (uniform_mask || e.n_smem > kTableCap) return false;
     if (W != 32 && W != 64) {  // other lengths: the two-chromosome schedule with masked lanes, no table loop
         const bool table = e.n > 0 && e.semantics != TF_SEM_NONE;
-        if (W < 3 || W > 128 || table || g_stream_schedule == 1) return false;
+        if (W < 3 || W > 256 || table || g_stream_schedule == 1) return false;
     }
     return stream_smem_bytes(e, W) <= 200 * 1024;
 }
