@@ -305,3 +305,48 @@ def test_evolve_batch_resume_is_bit_identical(tf, tmp_path):
     # emergency stop hook (HR:110-112)
     calls = []
     assert B.evolve_batch(pop, env, 50, ga, should_stop=lambda: len(calls) >= 3 or calls.append(1)) is None
+
+
+def test_island_exchange_kernels_match_the_oracle(tf):
+    """The device side of an elite migration (islands.CudaOps: tf_rank_topk -> tf_pack_elites -> [all-gather] ->
+    tf_select_set -> tf_replace_worst) against the CPU restatement, with three islands emulated on one GPU (the
+    all-gather is a stack); then a single-island IslandGA run against the plain rank + generation loop."""
+    torch, L, B = tf
+    from tracefly_b200.islands import CudaOps, IslandGA
+    world, P, W, E = 3, 4001, 32, 37
+    rng = np.random.default_rng(12)
+    table = random_table(rng, 40, 48, sem_pf=True)
+    env, prm = B.Environment(L.SEM_PF, table, 0.0), L.default_params(dist_zero_guard=0)
+    pops = [B.init_walks(20 + r, P, W, start=(24, 24, 24), lo=(0, 0, 0), hi=(47, 47, 47)) for r in range(world)]
+    fits = [B.fitness_batch(p, None, env, prm, want_collisions=False)[0] for p in pops]
+    fits[1][::7] = fits[1][3]                                           # ties among elites and victims
+    ops = CudaOps(env, prm, P, W, 2, E, (world - 1) * E)
+    ref_pop = [p.cpu().numpy().copy() for p in pops]
+    ref_fit = [f.cpu().numpy().copy() for f in fits]
+    rows = torch.empty((world, E, W, 4), device="cuda")
+    rfit = torch.empty((world, E), device="cuda")
+    idx = torch.empty(E, dtype=torch.int32, device="cuda")
+    for r in range(world):
+        ops.elites(fits[r], idx)
+        ops.pack(pops[r], fits[r], idx, rows[r], rfit[r])
+    worst = torch.empty((world - 1) * E, dtype=torch.int32, device="cuda")
+    for r in range(world):
+        ops.worst(fits[r], worst)
+        ops.replace(pops[r], fits[r], worst, rows, rfit, world, r, E)
+    torch.cuda.synchronize()
+    packs = [O.pack_elites(ref_pop[r], ref_fit[r], O.topk(ref_fit[r], E)) for r in range(world)]
+    grows, gfit = np.stack([p[0] for p in packs]), np.stack([p[1] for p in packs])
+    assert np.array_equal(grows, rows.cpu().numpy()) and np.array_equal(gfit, rfit.cpu().numpy())
+    for r in range(world):
+        O.replace_worst(ref_pop[r], ref_fit[r], O.select_set(ref_fit[r], (world - 1) * E, worst=True), grows, gfit, world, r, E)
+        assert np.array_equal(ref_pop[r], pops[r].cpu().numpy()), f"island {r}: population differs"
+        assert np.array_equal(ref_fit[r], fits[r].cpu().numpy())
+    # one island: IslandGA.step == rank + fused generation
+    ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=3, mutation_rate=0.3)
+    start = B.init_walks(5, P, W, start=(24, 24, 24), lo=(0, 0, 0), hi=(47, 47, 47))
+    isl = IslandGA(start.clone(), ga, seed=9, env=env, params=prm)
+    pop, fit = start.clone(), B.fitness_batch(start, None, env, prm, want_collisions=False)[0]
+    for g in range(4):
+        isl.step()
+        pop, fit, *_ = B.generation(env, pop, fit, B.rank_topk(fit, 2), ga, prm, seed=9, generation=g)
+    assert isl.migrations == 0 and torch.equal(isl.pop, pop) and torch.equal(isl.fit, fit)
