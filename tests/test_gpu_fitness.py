@@ -171,6 +171,16 @@ def test_error_behaviour(tf):
         B.Environment(7, None, 0.0)
     fit, coll = B.fitness_batch(torch.zeros((0, 8, 4), device="cuda"), None, env)
     assert fit.numel() == 0
+    # the small misc entry points of the C-ABI
+    import ctypes as C
+    sms, major, minor, hbm = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+    assert L.lib.tf_device_info(C.byref(sms), C.byref(major), C.byref(minor), C.byref(hbm)) == 0
+    assert major.value == 10 and sms.value >= 100 and hbm.value > (100 << 30)
+    assert L.lib.tf_last_cuda_error() == 0
+    n0 = L.launch_count()
+    B.fitness_batch(torch.zeros((4, 8, 4), device="cuda"), None, env)
+    assert L.launch_count() == n0 + 1
+    assert L.lib.tf_set_option(99, 0) < 0 and L.lib.tf_set_option(L.OPT_STREAM_SCHEDULE, 3) < 0
 
 
 def test_dynamic_index_equals_brute_force(tf):
