@@ -1,16 +1,18 @@
-// tf_stream_dev.cuh — TMA-staged form of the FP32 fitness sweep / fused generation for
-// chromosomes of exactly 32*NW waypoints (the BASELINE configs: W = 32, 64).
+// tf_stream_dev.cuh — TMA-staged form of the FP32 fitness sweep / fused generation for fixed-length
+// chromosomes (no ragged lengths, no uniform crossover), in two warp schedules:
+//   stream_kernel  one chromosome per warp step; W = 32 NW exactly (W = 32, 64); the variants WITH an obstacle table;
+//   duo_kernel     two chromosomes per warp step (one per half-warp), dynamic tile tickets; the variants WITHOUT a
+//                  table; runtime row length (3 <= W <= 256, masked lanes) on top of the exact-W form.
 //
 // Same tile structure and the SAME arithmetic (bit-identical results) as fitness_kernel /
 // generation_kernel, but the rows never pass through the LSU on the way in:
-//   * each warp owns a ring of kStages row buffers in shared memory, each with its own mbarrier;
-//   * one elected lane issues, kStages-2 chromosomes ahead, the 1-D TMA bulk copies that gather a
+//   * each warp owns a ring of kStages row buffers in shared memory with mbarriers;
+//   * the lane that owns a child issues, from its own plan registers, the 1-D TMA bulk copies that gather the
 //     child's two parent pieces ([0,cp) of one parent, [cp,W) of the other) straight into a ring
 //     slot (cp.async.bulk ... mbarrier::complete_tx — SASS UBLKCP);
-//   * the mutation is applied in shared memory, the voxel gathers of chromosome c+1 are issued
-//     before chromosome c is evaluated, and the neighbour waypoint is a second LDS instead of
-//     three shuffles.
-// What is in flight is now bounded by shared memory (kStages-2 KB-sized rows per warp), not by
+//   * the mutation is applied in shared memory and the neighbour waypoint is a second LDS instead of
+//     three shuffles; stream_kernel also issues the voxel gathers of chromosome c+1 before c is evaluated.
+// What is in flight is bounded by shared memory (kStages KB-sized rows per warp), not by
 // registers, so the DRAM latency of the random parent gathers is hidden at 32 warps / SM.
 #pragma once
 #include "tf_fitness_dev.cuh"
