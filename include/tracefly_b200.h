@@ -108,7 +108,7 @@ int tf_env_dynamic_index_stats(const tf_env* env, int64_t* n_lists, int64_t* n_o
 /* Bit-packed occupancy grid in BRICK layout (see tf_voxel_*): caller-owned device memory,
  * must stay alive while the env uses it.  nx, ny, nz multiples of 8.  NULL detaches. */
 int tf_env_set_voxels(tf_env* env, const uint32_t* bricks_dev, int nx, int ny, int nz);
-/* Hazard heat-map f32[nt][ny][nx] on the device; the env keeps its own (transposed) copy, so the
+/* Hazard heat-map f32[nt][ny][nx] on the device; the env keeps its own (corner-packed, transposed) copy, so the
  * caller's buffer may be released after the call.  A waypoint i at (x, y)
  * samples tri-linearly at gx = x*sx + ox, gy = y*sy + oy, gt = i*st (clamped).  NULL detaches. */
 int tf_env_set_hazard(tf_env* env, const float* hazard_dev, int nt, int ny, int nx,
@@ -203,7 +203,9 @@ typedef struct tf_ga_params {
     float mutation_rate;   /* HR:62: 0.1 */
     float sigma;           /* TF_MUT_GAUSSIAN */
     uint32_t stream_id;    /* Philox counter word 2: island / rank id */
-    int32_t _pad;
+    int32_t reserve_sms;   /* tf_generation only: SMs (0 = none, at most half) this launch of the persistent kernel
+                              leaves unoccupied, so that kernels on other streams (elite selection, NCCL) run beside
+                              it.  A launch argument, not library state: safe with several host threads / streams. */
 } tf_ga_params;
 
 void tf_ga_params_default(tf_ga_params* p);
@@ -323,9 +325,8 @@ int tf_selftest_sqrt(uint32_t first_bits, uint64_t count, uint64_t* mismatches_d
  * 2 = two (one per half-warp, dynamic tile tickets), 0 (default) = the library picks per kernel variant.
  * Bit-identical results either way; exposed for A/B measurements and the equivalence tests. */
 #define TF_OPT_STREAM_SCHEDULE 2
-/* TF_OPT_RESERVE_SMS: number of SMs (0 = none, at most half) that the persistent, dynamically scheduled
- * kernels leave unoccupied, so that kernels on other streams (elite selection, NCCL) run beside them instead
- * of waiting for the whole grid to drain.  Read at launch time. */
+/* TF_OPT_RESERVE_SMS: process-wide DEFAULT of tf_ga_params.reserve_sms (the larger of the two applies).  Prefer
+ * the per-launch field: an option toggled around a launch races with other host threads. */
 #define TF_OPT_RESERVE_SMS 3
 int tf_set_option(int option, int value);
 /* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */

@@ -85,4 +85,7 @@ def test_generate_local_path_files(hr, tmp_path, monkeypatch):
     out = json.load(open("data/ga_path_output.json"))
     assert set(out) == {"path", "start", "end", "timestamp"}      # HR:148-153
     assert [tuple(w) for w in out["path"]] == best and best[0] == (0.0, 0.0, 0.0)
-    assert hr.generate_local_path((0, 0, 0), (6, 5, 2))[-1] in [(6, 5, 2), (5, 4, 2), (6, 4, 2), (5, 5, 2), (6, 5, 1), (6, 5, 3)] or True
+    # the module-level function (HR:138): endpoints are never mutated (HR:95 picks interior waypoints, crossover keeps
+    # both ends), and the diagonal walk to (6, 5, 2) has Chebyshev distance 6 -> 7 waypoints (HR:68-80)
+    p = hr.generate_local_path((0, 0, 0), (6, 5, 2))
+    assert p[0] == (0, 0, 0) and p[-1] == (6, 5, 2) and len(p) == 7

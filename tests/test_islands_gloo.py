@@ -83,39 +83,10 @@ def _worker(rank, world, port, outdir, pipelined):
 
 
 def _simulate(world, pipelined):
-    """Single-process restatement of the island schedule.  Pipelined: the elites of generation g
-    (g % INTERVAL == 0) replace the worst of generation g+1 (victims in ascending index order)."""
-    from oracle import c_oracle as O
-    st = []
-    for r in range(world):
-        _, oenv, pop = _world(r)
-        st.append(dict(env=oenv, pop=pop, fit=O.fitness_f32(oenv, pop)[0]))
-    pending = None
-
-    def insert(packs):
-        grows = np.stack([p[0] for p in packs])
-        gfit = np.stack([p[1] for p in packs])
-        for r, s in enumerate(st):
-            worst = O.select_set(s["fit"], (world - 1) * E, worst=True)
-            O.replace_worst(s["pop"], s["fit"], worst, grows, gfit, world, r, E)
-
-    for gen in range(GENS):
-        for r, s in enumerate(st):
-            ga = O.default_ga(selection=1, tournament_k=3, mutation_rate=0.3, stream_id=r)
-            s["pop"], _, _, _ = O.ga_step(s["pop"], s["fit"], O.topk(s["fit"], 2), ga, seed=SEED, gen=gen)
-            s["fit"] = O.fitness_f32(s["env"], s["pop"])[0]
-        if pending is not None:
-            insert(pending)
-            pending = None
-        if (gen + 1) % INTERVAL == 0:
-            packs = [O.pack_elites(s["pop"], s["fit"], O.topk(s["fit"], E)) for s in st]
-            if pipelined:
-                pending = packs
-            else:
-                insert(packs)
-    if pending is not None:
-        insert(pending)
-    return st
+    """The single-process restatement of the island schedule (oracle/islands_sim.py) on this test's world."""
+    from oracle import islands_sim
+    return islands_sim.simulate(world, lambda r: (_world(r)[1], None, _world(r)[2]),
+                                dict(selection=1, tournament_k=3, mutation_rate=0.3), SEED, GENS, INTERVAL, E, pipelined)
 
 
 @pytest.mark.parametrize("pipelined", [True, False])

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libtracefly_b200.so")
+# TRACEFLY_B200_LIB: load another build of the SAME library (A/B measurements of kernel variants, build.py)
+LIB_PATH = os.environ.get("TRACEFLY_B200_LIB") or os.path.join(_HERE, "_build", "libtracefly_b200.so")
 
 TF_OK = 0
 TF_ERR_INVALID, TF_ERR_SHAPE, TF_ERR_UNSUPPORTED, TF_ERR_CUDA = -1, -2, -3, -4
@@ -31,7 +32,7 @@ class Params(C.Structure):  # tf_params
 class GaParams(C.Structure):  # tf_ga_params
     _fields_ = [("n_elite", C.c_int32), ("selection", C.c_int32), ("n_top", C.c_int32), ("tournament_k", C.c_int32),
                 ("crossover", C.c_int32), ("mutation", C.c_int32), ("mutation_rate", C.c_float), ("sigma", C.c_float),
-                ("stream_id", C.c_uint32), ("_pad", C.c_int32)]
+                ("stream_id", C.c_uint32), ("reserve_sms", C.c_int32)]
 
 
 if not os.path.exists(LIB_PATH):

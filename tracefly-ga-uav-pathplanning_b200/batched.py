@@ -581,6 +581,9 @@ class HostStepper:
         if s["busy"]:
             raise RuntimeError("HostStepper: collect the oldest result before submitting more work")
         n4 = self.P * self.W
+        # the environment (voxel grid, candidate indices, hazard map) and the caller's earlier work may still be in
+        # flight on the caller's stream; the stepper's own streams do not synchronise with it implicitly
+        s["stream"].wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s["stream"]):
             if self.fmt == "f32":
                 s["pop"].copy_(host_pop, non_blocking=True)

@@ -17,26 +17,37 @@ long long g_launch_count = 0;
 int g_disable_stream = 0;
 int g_stream_schedule = 0;
 int g_reserve_sms = 0;
-static int g_sm_count = 0;
-static int g_dev_checked = 0;
+// per-device caches, keyed by the CURRENT device of the calling thread (one process may drive several GPUs)
+constexpr int kMaxDev = 64;
+static int g_sm_count[kMaxDev] = {0};
+static signed char g_dev_checked[kMaxDev] = {0};
 
 int ensure_device() {
-    if (g_dev_checked) return g_dev_checked > 0 ? TF_OK : TF_ERR_NODEVICE;
     int dev = 0;
-    cudaDeviceProp prop;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) {
         cudaGetLastError();
-        g_dev_checked = -1;  // no sm_100 device: there is deliberately no fallback
         return TF_ERR_NODEVICE;
     }
-    g_sm_count = prop.multiProcessorCount;
-    g_dev_checked = 1;
+    if (g_dev_checked[dev]) return g_dev_checked[dev] > 0 ? TF_OK : TF_ERR_NODEVICE;
+    int major = 0, sms = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || major != 10) {
+        cudaGetLastError();
+        g_dev_checked[dev] = -1;  // no sm_100 device: there is deliberately no fallback
+        return TF_ERR_NODEVICE;
+    }
+    g_sm_count[dev] = sms;
+    g_dev_checked[dev] = 1;
     return TF_OK;
 }
-int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+int sm_count() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return 148;
+    return g_sm_count[dev] > 0 ? g_sm_count[dev] : 148;
+}
 
 int* sched_slot() {
-    constexpr int kSlots = 4096, kMaxDev = 64;
+    constexpr int kSlots = 4096;
     static int* rings[kMaxDev] = {nullptr};
     static unsigned next[kMaxDev] = {0};
     static std::mutex mu;
@@ -122,8 +133,7 @@ constexpr int kIdxThreads = 128;
 constexpr int kIdxMaxPerThread = 16;  // n_dyn <= 2048
 __global__ void __launch_bounds__(kIdxThreads)
 build_dyn_index_kernel(const float4* __restrict__ dynA, const float4* __restrict__ dynB, int n, int T, int band, int gx,
-                       int gy, int gz, float ox, float oy, float oz, float h, int cap, int32_t* __restrict__ cand,
-                       int32_t* __restrict__ count) {
+                       int gy, int gz, float ox, float oy, float oz, float h, int cap, uint16_t* __restrict__ cand) {
     __shared__ float red[kIdxThreads];
     __shared__ int n_list;
     const size_t ncell = (size_t)gx * gy * gz;
@@ -165,11 +175,26 @@ build_dyn_index_kernel(const float4* __restrict__ dynA, const float4* __restrict
     for (int k = threadIdx.x; k < n; k += kIdxThreads, ++j) {
         if ((marked >> j) & 1u) {
             const int pos = atomicAdd(&n_list, 1);
-            if (pos < cap) cand[cellid * cap + pos] = k;
+            if (pos < cap - 1) cand[cellid * cap + 1 + pos] = (uint16_t)(2 * k);   // word 0 of a list is its length
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) count[cellid] = n_list <= cap ? n_list : -1;
+    if (threadIdx.x == 0) {
+        cand[cellid * cap] = (uint16_t)(n_list <= cap - 1 ? n_list : 0xffff);
+        // the walk reads whole groups of entries ({1..3}, {4..7}, ...) without per-entry predicates: fill the last
+        // group with copies of the first entry (min / or are idempotent)
+        if (n_list > 0 && n_list <= cap - 1)
+            for (int pos = n_list; ((pos + 1) & 3) != 0; ++pos) cand[cellid * cap + 1 + pos] = cand[cellid * cap + 1];
+    }
+}
+
+// The moving spheres as interleaved 32-byte records (c0, r2 | v, 0): one sector per sphere.
+__global__ void dyn_records_kernel(const float4* __restrict__ dynA, const float4* __restrict__ dynB, int n,
+                                   float4* __restrict__ rec) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    rec[2 * k] = dynA[k];
+    rec[2 * k + 1] = dynB[k];
 }
 
 // ------------------------------------------------------------------ static candidate index
@@ -288,13 +313,15 @@ build_cyl_index_kernel(const __grid_constant__ EnvDev e, int nz, float oz, float
     if (threadIdx.x == 0) count[c] = n_list <= cap ? n_list : -1;
 }
 
-// [t][y][x] -> [y][x][t]
-__global__ void hazard_transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int nt, size_t nyx) {
-    const size_t n = nyx * (size_t)nt;
+// [t][y][x] -> corner-packed [y][x][t]: (v[t][y][x], v[t][y][x1], v[t1][y][x], v[t1][y][x1]), x1 / t1 clamped
+__global__ void hazard_pack_kernel(const float* __restrict__ in, float4* __restrict__ out, int nt, int ny, int nx) {
+    const size_t nyx = (size_t)ny * nx, n = nyx * (size_t)nt;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const size_t c = i / nt;
-        const int t = (int)(i - c * nt);
-        out[i] = in[(size_t)t * nyx + c];
+        const int t = (int)(i - c * nt), x = (int)(c % nx);
+        const size_t c1 = x + 1 < nx ? c + 1 : c;
+        const size_t t1 = t + 1 < nt ? t + 1 : t;
+        out[i] = make_float4(in[(size_t)t * nyx + c], in[(size_t)t * nyx + c1], in[t1 * nyx + c], in[t1 * nyx + c1]);
     }
 }
 
@@ -395,7 +422,7 @@ extern "C" int tf_env_set_dynamic(tf_env* env, const tf_dyn_obstacle* dyn_host, 
     if (env->dyn_block) { cudaFree(env->dyn_block); env->dyn_block = nullptr; }
     env->d.n_dyn = env->d.n_dyn_smem = 0; env->d.dynA = env->d.dynB = nullptr;
     if (env->dindex_block) { cudaFree(env->dindex_block); env->dindex_block = nullptr; }
-    env->d.dcand = env->d.dcount = nullptr;
+    env->d.dcand = nullptr; env->d.drec = nullptr;
     if (n == 0) return TF_OK;
     std::vector<float> A((size_t)n * 4), B((size_t)n * 4);
     for (int i = 0; i < n; ++i) {
@@ -420,8 +447,23 @@ extern "C" int tf_env_build_dynamic_index(tf_env* env, int time_slices, int band
     if (env->d.n_dyn <= 0) return TF_ERR_INVALID;
     if (time_slices < 1 || time_slices > 4096 || band < 1 || cell <= 0.0f || cap < 1 || cap > 1024) return TF_ERR_SHAPE;
     if (env->d.n_dyn > kIdxThreads * kIdxMaxPerThread) return TF_ERR_SHAPE;
+    // the kernels take the band of a time by multiply-shift; where that is not exact for every t < time_slices the
+    // band is widened to the next power of two (always exact; the index is built for the band actually used)
+    auto band_magic = [&](int b) {
+        uint32_t m = (uint32_t)(((1u << 20) + (uint32_t)b - 1u) / (uint32_t)b);
+        for (int t = 0; t < time_slices && m; ++t)
+            if ((((uint32_t)t * m) >> 20) != (uint32_t)(t / b)) m = 0;
+        return m;
+    };
+    uint32_t magic = band_magic(band);
+    if (magic == 0) {
+        int b2 = 1;
+        while (b2 < band) b2 <<= 1;
+        band = b2;
+        magic = band_magic(band);
+    }
     const int nbands = (time_slices + band - 1) / band;
-    cap = (cap + 3) & ~3;  // lists are read as int4
+    cap = (cap + 1 + 7) & ~7;  // word 0 of a list is its length; lists are rows of 16-bit words read 16 bytes at a time
     int g[3];
     for (int a = 0; a < 3; ++a) {
         if (!(box_hi[a] > box_lo[a])) return TF_ERR_SHAPE;
@@ -434,22 +476,21 @@ extern "C" int tf_env_build_dynamic_index(tf_env* env, int time_slices, int band
     int rc = ensure_device();
     if (rc != TF_OK) return rc;
     if (env->dindex_block) { cudaFree(env->dindex_block); env->dindex_block = nullptr; }
-    env->d.dcand = env->d.dcount = nullptr;
-    const size_t bytes_count = ((nlist * 4 + 255) / 256) * 256, bytes_cand = nlist * (size_t)cap * 4;
-    TF_CUDA(cudaMalloc(&env->dindex_block, bytes_count + bytes_cand));
-    int32_t* count = (int32_t*)env->dindex_block;
-    int32_t* cand = (int32_t*)((char*)env->dindex_block + bytes_count);
+    env->d.dcand = nullptr; env->d.drec = nullptr;
+    const size_t bytes_rec = (((size_t)env->d.n_dyn * 32 + 255) / 256) * 256, bytes_cand = nlist * (size_t)cap * 2;
+    TF_CUDA(cudaMalloc(&env->dindex_block, bytes_rec + bytes_cand));
+    float4* rec = (float4*)env->dindex_block;
+    uint16_t* cand = (uint16_t*)((char*)env->dindex_block + bytes_rec);
     build_dyn_index_kernel<<<(unsigned)nlist, kIdxThreads, 0, (cudaStream_t)stream>>>(
         env->d.dynA, env->d.dynB, env->d.n_dyn, time_slices, band, g[0], g[1], g[2], box_lo[0], box_lo[1], box_lo[2], cell,
-        cap, cand, count);
+        cap, cand);
+    TF_LAUNCH_CHECK();
+    dyn_records_kernel<<<(env->d.n_dyn + 255) / 256, 256, 0, (cudaStream_t)stream>>>(env->d.dynA, env->d.dynB, env->d.n_dyn, rec);
     TF_LAUNCH_CHECK();
     TF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    env->d.dcand = cand; env->d.dcount = count;
+    env->d.dcand = cand; env->d.drec = rec;
     env->d.dT = time_slices; env->d.dband = band; env->d.dgx = g[0]; env->d.dgy = g[1]; env->d.dgz = g[2]; env->d.dcap = cap;
     env->d.dox = box_lo[0]; env->d.doy = box_lo[1]; env->d.doz = box_lo[2]; env->d.dinv_h = 1.0f / cell;
-    uint32_t magic = (uint32_t)(((1u << 20) + (uint32_t)band - 1u) / (uint32_t)band);
-    for (int t = 0; t < time_slices && magic; ++t)
-        if ((((uint32_t)t * magic) >> 20) != (uint32_t)(t / band)) magic = 0;
     env->d.dband_magic = magic;
     env->d.n_dyn_smem = 0;  // the kernels read the records through L1 / L2 now
     return TF_OK;
@@ -457,15 +498,15 @@ extern "C" int tf_env_build_dynamic_index(tf_env* env, int time_slices, int band
 
 extern "C" int tf_env_dynamic_index_stats(const tf_env* env, int64_t* n_lists, int64_t* n_overflow, double* mean_len,
                                           int* max_len) {
-    if (!env || !env->d.dcount) return TF_ERR_INVALID;
+    if (!env || !env->d.dcand) return TF_ERR_INVALID;
     const size_t n = (size_t)((env->d.dT + env->d.dband - 1) / env->d.dband) * env->d.dgx * env->d.dgy * env->d.dgz;
-    std::vector<int32_t> h(n);
-    TF_CUDA(cudaMemcpy(h.data(), env->d.dcount, n * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint16_t> h(n);
+    TF_CUDA(cudaMemcpy2D(h.data(), 2, env->d.dcand, (size_t)env->d.dcap * 2, 2, n, cudaMemcpyDeviceToHost));
     int64_t over = 0;
     double sum = 0.0;
     int mx = 0;
     for (size_t i = 0; i < n; ++i) {
-        if (h[i] < 0) ++over;
+        if (h[i] == 0xffff) ++over;
         else { sum += h[i]; if (h[i] > mx) mx = h[i]; }
     }
     if (n_lists) *n_lists = (int64_t)n;
@@ -565,15 +606,15 @@ extern "C" int tf_env_set_hazard(tf_env* env, const float* hazard_dev, int nt, i
     if (nt <= 0 || ny <= 0 || nx <= 0) return TF_ERR_SHAPE;
     int rc = ensure_device();
     if (rc != TF_OK) return rc;
-    // the env owns a transposed copy [y][x][t] (see hazard_sample); the caller's tensor is not kept
+    // the env owns a corner-packed copy in [y][x][t] order (see hazard_sample); the caller's tensor is not kept
     const size_t n = (size_t)nt * ny * nx;
-    if (n >= ((size_t)1 << 31)) return TF_ERR_SHAPE;  // the kernels index the map with 32 bits
-    TF_CUDA(cudaMalloc(&env->hazard_block, n * 4));
-    hazard_transpose_kernel<<<(unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256>>>(
-        hazard_dev, (float*)env->hazard_block, nt, (size_t)ny * nx);
+    if (n >= ((size_t)1 << 29)) return TF_ERR_SHAPE;  // the kernels index the packed map with 32 bits
+    TF_CUDA(cudaMalloc(&env->hazard_block, n * 16));
+    hazard_pack_kernel<<<(unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256>>>(
+        hazard_dev, (float4*)env->hazard_block, nt, ny, nx);
     TF_LAUNCH_CHECK();
     TF_CUDA(cudaDeviceSynchronize());
-    env->d.hazard = (const float*)env->hazard_block;
+    env->d.hazard = (const float4*)env->hazard_block;
     env->d.nt = nt; env->d.hny = ny; env->d.hnx = nx;
     env->d.sx = sx; env->d.sy = sy; env->d.ox = ox; env->d.oy = oy; env->d.st = st;
     return TF_OK;
@@ -645,7 +686,7 @@ extern "C" void tf_ga_params_default(tf_ga_params* p) {
     p->mutation_rate = 0.1f;  // HR:62
     p->sigma = 1.0f;
     p->stream_id = 0;
-    p->_pad = 0;
+    p->reserve_sms = 0;
 }
 
 extern "C" int tf_version(void) { return TF_VERSION; }

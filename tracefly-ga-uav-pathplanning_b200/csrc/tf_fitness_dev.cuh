@@ -227,73 +227,142 @@ __device__ __forceinline__ void dyn_test(const float4 o, const float4 v, float x
     m2 = fminf(m2, d2);
 }
 
+// One listed sphere against one point: `rec` is the sphere's offset into the interleaved record table
+// drec[2 k] = (c0, r2), drec[2 k + 1] = (v, 0) — 32 bytes, one sector — which is what the lists store.  The
+// table (32 KB for 1024 spheres) stays in L1, and the lanes of a half-warp (consecutive waypoints, mostly the
+// same cell) read the same record.  Same arithmetic as dyn_test.
+__device__ __forceinline__ void dyn_test_rec(const float4* __restrict__ drec, int rec, float x, float y, float z, float tm,
+                                             bool& hit, float& m2) {
+    dyn_test(__ldg(drec + (uint32_t)rec), __ldg(drec + (uint32_t)rec + 1), x, y, z, tm, hit, m2);
+}
+
+// Cell of the candidate index for a point at integer time ti, or -1 (outside the index box / time range).
+__device__ __forceinline__ int dyn_cell(const EnvDev& e, float x, float y, float z, int ti) {
+    const int ix = __float2int_rd((x - e.dox) * e.dinv_h), iy = __float2int_rd((y - e.doy) * e.dinv_h),
+              iz = __float2int_rd((z - e.doz) * e.dinv_h);
+    const bool indexed = ti >= 0 && ti < e.dT && (unsigned)ix < (unsigned)e.dgx && (unsigned)iy < (unsigned)e.dgy &&
+                         (unsigned)iz < (unsigned)e.dgz;
+    if (!indexed) return -1;
+    const uint32_t tb = ((uint32_t)ti * e.dband_magic) >> 20;   // == ti / dband for every ti < dT (checked at build time)
+    // < 2^26 lists (tf_env_build_dynamic_index)
+    return (int)(((tb * (uint32_t)e.dgz + (uint32_t)iz) * (uint32_t)e.dgy + (uint32_t)iy) * (uint32_t)e.dgx + (uint32_t)ix);
+}
+
+// A point outside the index (or in an overflowed cell): every sphere, from global memory.  Rare by construction
+// (tf_env_build_dynamic_index asks for a generous box): a rolled loop, so that the hot kernels stay small.
+__device__ __forceinline__ void dyn_brute_force(const float4* __restrict__ dynA, const float4* __restrict__ dynB, int n, float x,
+                                             float y, float z, float tm, bool& hit, float& m2) {
+    bool h = hit;
+    float m = m2;
+#pragma unroll 1
+    for (int k = 0; k < n; ++k) dyn_test(__ldg(dynA + k), __ldg(dynB + k), x, y, z, tm, h, m);
+    hit = h;
+    m2 = m;
+}
+
+// The list of `cell` (head = its first 16 bytes, already loaded) against one point at integer time ti.
+// A list is a row of 16-bit words: word 0 = length (0xffff = overflow), words 1.. = 2 * sphere id (the offset of
+// its record in drec); the entries come in groups {1..3}, {4..7}, {8..11}, ... and the last group of a list is
+// filled up with copies of its first entry (min / or are idempotent), so a group is walked without per-entry
+// predicates and its loads go out together.  Lists of up to 7 spheres need no second list load.
+__device__ __forceinline__ void dyn_group(const EnvDev& e, uint32_t w0, uint32_t w1, float x, float y, float z, float tm,
+                                          bool& h, float& m2) {
+    dyn_test_rec(e.drec, (int)(w0 & 0xffffu), x, y, z, tm, h, m2);
+    dyn_test_rec(e.drec, (int)(w0 >> 16), x, y, z, tm, h, m2);
+    dyn_test_rec(e.drec, (int)(w1 & 0xffffu), x, y, z, tm, h, m2);
+    dyn_test_rec(e.drec, (int)(w1 >> 16), x, y, z, tm, h, m2);
+}
+__device__ __forceinline__ void dyn_walk(const EnvDev& e, int cell, const uint4 hd, float x, float y, float z, int ti, bool& h,
+                                         float& m2) {
+    const float tm = (float)ti;
+    const int n = (int)(hd.x & 0xffffu);
+    if (n != 0xffff) {
+        if (n > 0) {
+            dyn_test_rec(e.drec, (int)(hd.x >> 16), x, y, z, tm, h, m2);
+            dyn_test_rec(e.drec, (int)(hd.y & 0xffffu), x, y, z, tm, h, m2);
+            dyn_test_rec(e.drec, (int)(hd.y >> 16), x, y, z, tm, h, m2);
+        }
+        if (n > 3) dyn_group(e, hd.z, hd.w, x, y, z, tm, h, m2);
+        if (n > 7) {
+            const uint4* list = reinterpret_cast<const uint4*>(e.dcand + (size_t)(uint32_t)cell * (uint32_t)e.dcap) + 1;
+#pragma unroll 1
+            for (int j = 7; j < n; j += 8, ++list) {
+                const uint4 q = __ldg(list);
+                dyn_group(e, q.x, q.y, x, y, z, tm, h, m2);
+                if (j + 4 < n) dyn_group(e, q.z, q.w, x, y, z, tm, h, m2);
+            }
+        }
+    } else {
+        dyn_brute_force(e.dynA, e.dynB, e.n_dyn, x, y, z, tm, h, m2);
+    }
+}
+__device__ __forceinline__ uint4 dyn_head(const EnvDev& e, int cell) {
+    uint4 head = make_uint4(0xffffu, 0, 0, 0);
+    if (cell >= 0) head = __ldg(reinterpret_cast<const uint4*>(e.dcand + (size_t)(uint32_t)cell * (uint32_t)e.dcap));
+    return head;
+}
+
+// Moving spheres against NP points whose times are the INTEGERS t0, t0 + dt, ... (waypoint indices).
+// Without a candidate index: brute force over the records staged in shared memory.  With one: a list is
+// 16-byte aligned and starts with its length, so the first load of a waypoint brings the length and the first
+// seven entries.  The walk is a chain of two dependent loads (list head -> records); the head of slot s + 1 is
+// requested before slot s is walked.
 template <int NP>
 __device__ __forceinline__ void eval_dynamic(const EnvDev& e, const Tables& t, const float (&x)[NP],
-                                             const float (&y)[NP], const float (&z)[NP], const float (&tm)[NP],
+                                             const float (&y)[NP], const float (&z)[NP], int t0, int dt,
                                              uint32_t& hit, float (&m2)[NP]) {
-    if (e.dcand == nullptr) {  // records staged in shared memory: brute force, all slots per record
+    if (e.dcand == nullptr) {
         for (int k = 0; k < e.n_dyn; ++k) {
             const float4 o = t.dA[k];
             const float4 v = t.dB[k];
 #pragma unroll
             for (int s = 0; s < NP; ++s) {
                 bool h = false;
-                dyn_test(o, v, x[s], y[s], z[s], tm[s], h, m2[s]);
+                dyn_test(o, v, x[s], y[s], z[s], (float)(t0 + dt * s), h, m2[s]);
                 hit |= h ? (1u << s) : 0u;
             }
         }
         return;
     }
-    // Candidate lists.  The list walk is a chain of dependent loads (count -> ids -> records) that mostly hit
-    // L2 on a spread-out population, so the independent parts go first: all NP cells and counts, then the
-    // first four ids of every list (lists are 16-byte aligned: cap % 4 == 0), and ids are read four at a time.
-    int cnt[NP];
-    uint32_t cell[NP];
+    int cell = dyn_cell(e, x[0], y[0], z[0], t0);
+    uint4 head = dyn_head(e, cell);
 #pragma unroll
     for (int s = 0; s < NP; ++s) {
-        const int ti = (int)tm[s];
-        const int ix = __float2int_rd((x[s] - e.dox) * e.dinv_h), iy = __float2int_rd((y[s] - e.doy) * e.dinv_h),
-                  iz = __float2int_rd((z[s] - e.doz) * e.dinv_h);
-        const bool indexed = (float)ti == tm[s] && ti >= 0 && ti < e.dT && (unsigned)ix < (unsigned)e.dgx &&
-                             (unsigned)iy < (unsigned)e.dgy && (unsigned)iz < (unsigned)e.dgz;
-        cnt[s] = -1;
-        cell[s] = 0;  // < 2^26 lists (tf_env_build_dynamic_index)
-        if (indexed) {
-            const uint32_t tb = e.dband_magic ? ((uint32_t)ti * e.dband_magic) >> 20 : (uint32_t)(ti / e.dband);
-            cell[s] = ((tb * (uint32_t)e.dgz + (uint32_t)iz) * (uint32_t)e.dgy + (uint32_t)iy) * (uint32_t)e.dgx + (uint32_t)ix;
-            cnt[s] = __ldg(e.dcount + cell[s]);
+        const uint4 hd = head;
+        const int cur_cell = cell, ti = t0 + dt * s;
+        if (s + 1 < NP) {
+            cell = dyn_cell(e, x[s + 1], y[s + 1], z[s + 1], ti + dt);
+            head = dyn_head(e, cell);
         }
-    }
-    constexpr bool kAhead = NP <= 4;  // more slots than that would only spill the prefetched ids
-    int4 first[kAhead ? NP : 1];
-    if constexpr (kAhead) {
-#pragma unroll
-        for (int s = 0; s < NP; ++s)
-            if (cnt[s] > 0) first[s] = __ldg(reinterpret_cast<const int4*>(e.dcand + (size_t)cell[s] * (uint32_t)e.dcap));
-    }
-#pragma unroll
-    for (int s = 0; s < NP; ++s) {
         bool h = false;
-        if (cnt[s] >= 0) {
-            const int4* list = reinterpret_cast<const int4*>(e.dcand + (size_t)cell[s] * (uint32_t)e.dcap);
-            const int n = cnt[s];
-            int4 q = make_int4(0, 0, 0, 0);
-            if (n > 0) q = kAhead ? first[kAhead ? s : 0] : __ldg(list);
-            for (int j = 0; j < n; j += 4) {
-                int4 nq = q;
-                if (j + 4 < n) nq = __ldg(list + (j >> 2) + 1);
-                dyn_test(__ldg(e.dynA + q.x), __ldg(e.dynB + q.x), x[s], y[s], z[s], tm[s], h, m2[s]);
-                if (j + 1 < n) dyn_test(__ldg(e.dynA + q.y), __ldg(e.dynB + q.y), x[s], y[s], z[s], tm[s], h, m2[s]);
-                if (j + 2 < n) dyn_test(__ldg(e.dynA + q.z), __ldg(e.dynB + q.z), x[s], y[s], z[s], tm[s], h, m2[s]);
-                if (j + 3 < n) dyn_test(__ldg(e.dynA + q.w), __ldg(e.dynB + q.w), x[s], y[s], z[s], tm[s], h, m2[s]);
-                q = nq;
-            }
-        } else {  // outside the index (or an overflowed cell): every sphere, from global memory
-            for (int k = 0; k < e.n_dyn; ++k)
-                dyn_test(__ldg(e.dynA + k), __ldg(e.dynB + k), x[s], y[s], z[s], tm[s], h, m2[s]);
-        }
+        dyn_walk(e, cur_cell, hd, x[s], y[s], z[s], ti, h, m2[s]);
         hit |= h ? (1u << s) : 0u;
     }
+}
+
+// One point at an arbitrary (fractional) time — the sample points of the S > 1 extension: brute force unless the
+// time happens to be an integer.
+__device__ __forceinline__ void eval_dynamic_point(const EnvDev& e, const Tables& t, float x, float y, float z, float tm,
+                                                   bool& hit, float& m2) {
+    const int ti = (int)tm;
+    if (e.dcand == nullptr || (float)ti == tm) {
+        const float xs[1] = {x}, ys[1] = {y}, zs[1] = {z};
+        float m[1] = {m2};
+        uint32_t hb = 0;
+        if (e.dcand == nullptr) {   // staged records: dyn_test at the exact time
+            for (int k = 0; k < e.n_dyn; ++k) {
+                bool h = false;
+                dyn_test(t.dA[k], t.dB[k], x, y, z, tm, h, m[0]);
+                hb |= h ? 1u : 0u;
+            }
+        } else {
+            eval_dynamic<1>(e, t, xs, ys, zs, ti, 0, hb, m);
+        }
+        hit = hit || hb != 0u;
+        m2 = m[0];
+        return;
+    }
+    for (int k = 0; k < e.n_dyn; ++k) dyn_test(__ldg(e.dynA + k), __ldg(e.dynB + k), x, y, z, tm, hit, m2);
 }
 
 // Bit-packed occupancy probe through L2 (brick layout, include/tracefly_b200.h).
@@ -332,18 +401,18 @@ __device__ __forceinline__ float hazard_sample(const EnvDev& e, float x, float y
     gx = fminf(fmaxf(gx, 0.0f), (float)(e.hnx - 1));
     gy = fminf(fmaxf(gy, 0.0f), (float)(e.hny - 1));
     gt = fminf(fmaxf(gt, 0.0f), (float)(e.nt - 1));
-    int x0 = (int)gx, y0 = (int)gy, t0 = (int)gt;
-    int x1 = min(x0 + 1, e.hnx - 1), y1 = min(y0 + 1, e.hny - 1), t1 = min(t0 + 1, e.nt - 1);
-    float fx = __fsub_rn(gx, (float)x0), fy = __fsub_rn(gy, (float)y0), ft = __fsub_rn(gt, (float)t0);
-    // the env keeps the map transposed to [y][x][t]: the lanes of a warp are consecutive waypoints, i.e.
-    // nearly the same (x, y) at consecutive times, so their taps fall into the same cache lines.
-    // 32-bit element indices (the map has < 2^31 elements): one 64-bit address, small offsets for the taps
-    const float* c00 = e.hazard + (uint32_t)((y0 * e.hnx + x0) * e.nt + t0);
-    const int ox = (x1 - x0) * e.nt, oy = (y1 - y0) * e.hnx * e.nt, ot = t1 - t0;
-    float v000 = __ldg(c00), v001 = __ldg(c00 + ox), v010 = __ldg(c00 + oy), v011 = __ldg(c00 + oy + ox);
-    float v100 = __ldg(c00 + ot), v101 = __ldg(c00 + ox + ot), v110 = __ldg(c00 + oy + ot), v111 = __ldg(c00 + oy + ox + ot);
-    float a0 = lerp_f(lerp_f(v000, v001, fx), lerp_f(v010, v011, fx), fy);
-    float a1 = lerp_f(lerp_f(v100, v101, fx), lerp_f(v110, v111, fx), fy);
+    const int x0 = (int)gx, y0 = (int)gy, t0 = (int)gt;
+    const int y1 = min(y0 + 1, e.hny - 1);
+    const float fx = __fsub_rn(gx, (float)x0), fy = __fsub_rn(gy, (float)y0), ft = __fsub_rn(gt, (float)t0);
+    // the env keeps the map corner-packed in [y][x][t] order: one float4 holds the (x0, x1) x (t0, t1) taps of
+    // a row y (clamping of x1 / t1 folded in at pack time), so the 8 taps are 2 loads; the lanes of a warp are
+    // consecutive waypoints, i.e. nearly the same (x, y) at consecutive times: their taps share cache lines.
+    // 32-bit element indices (the packed map has < 2^29 elements)
+    const uint32_t col = (uint32_t)(x0 * e.nt + t0), rowlen = (uint32_t)(e.hnx * e.nt);
+    const float4 a = __ldg(e.hazard + ((uint32_t)y0 * rowlen + col));
+    const float4 b = __ldg(e.hazard + ((uint32_t)y1 * rowlen + col));
+    const float a0 = lerp_f(lerp_f(a.x, a.y, fx), lerp_f(b.x, b.y, fx), fy);
+    const float a1 = lerp_f(lerp_f(a.z, a.w, fx), lerp_f(b.z, b.w, fx), fy);
     return lerp_f(a0, a1, ft);
 }
 
@@ -352,16 +421,18 @@ __device__ __forceinline__ float hazard_sample(const EnvDev& e, float x, float y
 template <int SEM, bool VOX, int XF>
 __device__ __forceinline__ void eval_point_full(const EnvDev& e, const Tables& t, float x, float y, float z, float tm,
                                                 bool& hit_out, float& dnear) {
-    float xs[1] = {x}, ys[1] = {y}, zs[1] = {z}, tms[1] = {tm};
+    float xs[1] = {x}, ys[1] = {y}, zs[1] = {z};
     uint32_t hit = 0;
     float best[1] = {INFINITY};
     eval_static<SEM, 1>(e, t, xs, ys, zs, hit, best);
     float dn = (SEM == TF_SEM_HR) ? sqrt_rn(best[0]) : best[0];
     if constexpr (XF >= 1) {
         if (e.n_dyn > 0) {
-            float m2[1] = {INFINITY};
-            eval_dynamic<1>(e, t, xs, ys, zs, tms, hit, m2);
-            dn = fminf(dn, sqrt_rn(m2[0]));
+            float m2 = INFINITY;
+            bool dh = false;
+            eval_dynamic_point(e, t, x, y, z, tm, dh, m2);
+            hit |= dh ? 1u : 0u;
+            dn = fminf(dn, sqrt_rn(m2));
         }
     }
     if constexpr (VOX) hit |= voxel_hit(e, x, y, z) ? 1u : 0u;
@@ -467,13 +538,10 @@ __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_para
     for (int s = 0; s < NW; ++s) dn[s] = (SEM == TF_SEM_HR) ? sqrt_rn(acc.best[s]) : acc.best[s];
     if constexpr (XF >= 1) {
         if (e.n_dyn > 0) {
-            float m2[NW], tm[NW];
+            float m2[NW];
 #pragma unroll
-            for (int s = 0; s < NW; ++s) {
-                m2[s] = INFINITY;
-                tm[s] = (float)(lane + 32 * s);
-            }
-            eval_dynamic<NW>(e, t, cur.x, cur.y, cur.z, tm, hit, m2);
+            for (int s = 0; s < NW; ++s) m2[s] = INFINITY;
+            eval_dynamic<NW>(e, t, cur.x, cur.y, cur.z, lane, 32, hit, m2);
 #pragma unroll
             for (int s = 0; s < NW; ++s) dn[s] = fminf(dn[s], sqrt_rn(m2[s]));
         }

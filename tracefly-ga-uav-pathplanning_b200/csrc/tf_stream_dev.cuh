@@ -38,13 +38,10 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
     for (int s = 0; s < NW; ++s) dn[s] = (SEM == TF_SEM_HR) ? sqrt_rn(acc.best[s]) : acc.best[s];
     if constexpr (XF >= 1) {
         if (e.n_dyn > 0) {
-            float m2[NW], tm[NW];
+            float m2[NW];
 #pragma unroll
-            for (int s = 0; s < NW; ++s) {
-                m2[s] = INFINITY;
-                tm[s] = (float)(lane + 32 * s);
-            }
-            eval_dynamic<NW>(e, t, cur.x, cur.y, cur.z, tm, hit, m2);
+            for (int s = 0; s < NW; ++s) m2[s] = INFINITY;
+            eval_dynamic<NW>(e, t, cur.x, cur.y, cur.z, lane, 32, hit, m2);
 #pragma unroll
             for (int s = 0; s < NW; ++s) dn[s] = fminf(dn[s], sqrt_rn(m2[s]));
         }
@@ -269,12 +266,17 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 // are bit-identical (tests run both through TF_OPT_STREAM_SCHEDULE).
 // Tile bookkeeping: lanes 0-15 own children [0, T/2) of the tile, lanes 16-31 own [T/2, T); pair j =
 // children j and T/2 + j = lanes j and 16 + j, so every total ends in the half where its owner sits.
-// XF 1 (hazard map / moving spheres): 2 CTAs / SM = up to 128 registers; at 3 (80 registers) the candidate-list
-// loop spilled 250 bytes and cfg4 ran 8 % slower
+// XF 1 (hazard map / moving spheres): 3 CTAs / SM (80 registers; the tile sums spill 128 bytes to local memory,
+// outside the waypoint loops).  Round 2, cfg4 in the driver's regime (generation 6): 1.32 ms at 2 CTAs / SM
+// (128 registers), 1.25 ms at 3 — the kernel is latency- / issue-bound, not bandwidth-bound (profiles/README.md).
+// TF_DUO_XF1_CTAS is an A/B knob for build.py (TF_NVCC_EXTRA).
 // RAGW: the row length is a runtime value Wr <= 32 NW (any chromosome length up to 64 on the TMA-staged path);
 // lanes whose waypoint index is >= Wr are masked.  RAGW = false: W = 32 NW, the code of the BASELINE configs.
 template <int NW, int SEM, bool VOX, int XF, bool GA, bool RAGW>
-__global__ void __launch_bounds__(kBlockThreads, NW >= 8 ? 1 : NW >= 4 ? 2 : ((XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? 2 : 0)))
+#ifndef TF_DUO_XF1_CTAS
+#define TF_DUO_XF1_CTAS 3
+#endif
+__global__ void __launch_bounds__(kBlockThreads, NW >= 8 ? 1 : NW >= 4 ? 2 : ((XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? TF_DUO_XF1_CTAS : 0)))
 duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
            const __grid_constant__ tf_ga_params ga, const float4* __restrict__ pop,
            const float* __restrict__ fit, const int32_t* __restrict__ top_idx,
@@ -394,18 +396,28 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
                 }
                 __syncwarp();
             }
-            Lanes<NL> cur, prev;
+            // segment sums first (length, altitude, turns: they only need the row), so that the neighbour
+            // waypoints are dead before the gather-heavy part (voxels, moving spheres, hazard map) starts.
+            // per-lane partials of virtual lanes h (even m) and h + 16 (odd m), accumulated in waypoint order
+            Lanes<NL> cur;
+            float a_prox[2] = {0.0f, 0.0f}, a_dist[2] = {0.0f, 0.0f}, a_alt[2] = {0.0f, 0.0f}, a_haz[2] = {0.0f, 0.0f};
+            int turns = 0, ncoll = 0;
             float4* dst = GA ? next + (size_t)(slot0 + half * hT + j) * W : nullptr;
 #pragma unroll
             for (int m = 0; m < NL; ++m) {
-                const int k = h + 16 * m;
+                const int k = h + 16 * m, v = m & 1;
                 const bool ok = !RAGW || k < W;   // masked lanes sit at (-1, -1, -1): outside every grid
-                const float4 v = ok ? row[k] : make_float4(-1.0f, -1.0f, -1.0f, 0.0f);
-                const float4 q = ok ? row[k > 0 ? k - 1 : 0] : v;
-                cur.x[m] = v.x; cur.y[m] = v.y; cur.z[m] = v.z;
-                prev.x[m] = q.x; prev.y[m] = q.y; prev.z[m] = q.z;
+                const float4 c4 = ok ? row[k] : make_float4(-1.0f, -1.0f, -1.0f, 0.0f);
+                const float4 q = ok ? row[k > 0 ? k - 1 : 0] : c4;
+                cur.x[m] = c4.x; cur.y[m] = c4.y; cur.z[m] = c4.z;
                 if constexpr (GA) {
-                    if (live && ok) stg_stream_hint(dst + k, v, pol_stream);
+                    if (live && ok) stg_stream_hint(dst + k, c4, pol_stream);
+                }
+                if (ok && (m > 0 || h > 0)) {  // k >= 1
+                    const float dx = c4.x - q.x, dy = c4.y - q.y, dz = c4.z - q.z;
+                    a_dist[v] = __fadd_rn(a_dist[v], sqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
+                    a_alt[v] = __fadd_rn(a_alt[v], fabsf(dz));                      // HR:44
+                    if (RAGW ? k <= W - 2 : (m < NL - 1 || h < 15)) turns += (c4.x != q.x || c4.y != q.y) ? 1 : 0;  // k <= W-2, HR:38-40,43
                 }
             }
             VoxRegs<NL> vr;
@@ -414,46 +426,47 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
             acc.reset();
             if constexpr (SEM != TF_SEM_NONE) eval_static<SEM, NL>(e, tabs, cur.x, cur.y, cur.z, acc.hit, acc.best);
             uint32_t hit = acc.hit;
+            if constexpr (XF >= 1) {
+                // the hazard taps go out behind the voxel probes; then the probes are folded into `hit`, so that
+                // neither their words nor their masks are live during the candidate walk of the moving spheres
+                if (e.hazard != nullptr) {
+#pragma unroll
+                    for (int m = 0; m < NL; ++m) {
+                        const int k = h + 16 * m;
+                        if (RAGW && k >= W) continue;
+                        a_haz[m & 1] = __fadd_rn(a_haz[m & 1], hazard_sample(e, cur.x[m], cur.y[m], (float)k));
+                    }
+                }
+                if constexpr (VOX) {
+#pragma unroll
+                    for (int m = 0; m < NL; ++m) hit |= (vr.word[m] & vr.mask[m]) != 0u ? (1u << m) : 0u;
+                }
+            }
             float dn[NL];
 #pragma unroll
             for (int m = 0; m < NL; ++m) dn[m] = (SEM == TF_SEM_HR) ? sqrt_rn(acc.best[m]) : acc.best[m];
             if constexpr (XF >= 1) {
                 if (e.n_dyn > 0) {
-                    float m2[NL], tm[NL];
+                    float m2[NL];
 #pragma unroll
-                    for (int m = 0; m < NL; ++m) {
-                        m2[m] = INFINITY;
-                        tm[m] = (float)(h + 16 * m);
-                    }
-                    eval_dynamic<NL>(e, tabs, cur.x, cur.y, cur.z, tm, hit, m2);
+                    for (int m = 0; m < NL; ++m) m2[m] = INFINITY;
+                    eval_dynamic<NL>(e, tabs, cur.x, cur.y, cur.z, h, 16, hit, m2);
 #pragma unroll
                     for (int m = 0; m < NL; ++m) dn[m] = fminf(dn[m], sqrt_rn(m2[m]));
                 }
             }
-            // per-lane partials of virtual lanes h (even m) and h + 16 (odd m), accumulated in waypoint order
-            float a_prox[2] = {0.0f, 0.0f}, a_dist[2] = {0.0f, 0.0f}, a_alt[2] = {0.0f, 0.0f}, a_haz[2] = {0.0f, 0.0f};
-            int turns = 0, ncoll = 0;
             uint32_t cwords[NL];
+            if (has_dist) {
 #pragma unroll
-            for (int m = 0; m < NL; ++m) {
-                const int k = h + 16 * m, v = m & 1;
-                if (RAGW && k >= W) continue;
-                if (has_dist) a_prox[v] = __fadd_rn(a_prox[v], __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[m])));  // HR:46
-                if constexpr (XF >= 1) {
-                    if (e.hazard != nullptr) a_haz[v] = __fadd_rn(a_haz[v], hazard_sample(e, cur.x[m], cur.y[m], (float)k));
-                }
-                if (m > 0 || h > 0) {  // k >= 1
-                    const float px = prev.x[m], py = prev.y[m], pz = prev.z[m];
-                    const float dx = cur.x[m] - px, dy = cur.y[m] - py, dz = cur.z[m] - pz;
-                    a_dist[v] = __fadd_rn(a_dist[v], sqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
-                    a_alt[v] = __fadd_rn(a_alt[v], fabsf(dz));                      // HR:44
-                    if (RAGW ? k <= W - 2 : (m < NL - 1 || h < 15)) turns += (cur.x[m] != px || cur.y[m] != py) ? 1 : 0;  // k <= W-2, HR:38-40,43
+                for (int m = 0; m < NL; ++m) {
+                    if (RAGW && h + 16 * m >= W) continue;
+                    a_prox[m & 1] = __fadd_rn(a_prox[m & 1], __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[m])));  // HR:46
                 }
             }
 #pragma unroll
             for (int m = 0; m < NL; ++m) {
                 bool hm = (hit >> m) & 1u;
-                if constexpr (VOX) hm = hm || (vr.word[m] & vr.mask[m]) != 0u;
+                if constexpr (VOX && XF == 0) hm = hm || (vr.word[m] & vr.mask[m]) != 0u;
                 if (RAGW) hm = hm && h + 16 * m < W;
                 cwords[m] = __ballot_sync(0xffffffffu, hm);
                 ncoll += hm ? 1 : 0;
@@ -525,13 +538,14 @@ template <int NW, int SEM, bool VOX, int XF, bool GA, bool RAGW>
 static int launch_duo(const StreamArgs& a, size_t smem, int T) {
     auto kern = duo_kernel<NW, SEM, VOX, XF, GA, RAGW>;
     if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    static size_t occ_smem = ~(size_t)0;  // resident CTAs per SM of this variant with this much shared memory
-    static int occ_cached = 0;
-    int occ = occ_cached;
-    if (occ_smem != smem || occ <= 0) {
+    // resident CTAs per SM of this variant with this much shared memory.  One packed word (smem << 8 | occ): a
+    // racing thread at worst repeats the query; the answer is the same on every B200 of a node.
+    static unsigned long long occ_cache = 0;
+    const unsigned long long cached = __atomic_load_n(&occ_cache, __ATOMIC_RELAXED);
+    int occ = (int)(cached & 0xffu);
+    if ((cached >> 8) != (unsigned long long)smem || occ <= 0) {
         TF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlockThreads, smem));
-        occ_cached = occ;
-        occ_smem = smem;
+        __atomic_store_n(&occ_cache, ((unsigned long long)smem << 8) | (unsigned long long)(occ & 0xff), __ATOMIC_RELAXED);
     }
     const int resident_warps = sm_count() * max(occ, 1) * kWarpsPerBlock;
     // long runs (>= 4 tiles per resident warp): persistent grid, tickets from a global counter.  The plain fused
@@ -551,7 +565,8 @@ static int launch_duo(const StreamArgs& a, size_t smem, int T) {
         if (sched == nullptr) return TF_ERR_NOMEM;
         // TF_OPT_RESERVE_SMS: leave some SMs to kernels of other streams (the island model's elite exchange
         // runs beside the generation; a full persistent grid would hold every CTA slot until it ends)
-        grid = max(sm_count() - g_reserve_sms, sm_count() / 2) * max(occ, 1);
+        const int reserve = max(g_reserve_sms, (GA && a.ga) ? a.ga->reserve_sms : 0);
+        grid = max(sm_count() - max(reserve, 0), sm_count() / 2) * max(occ, 1);
     }
     kern<<<grid, kBlockThreads, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
                                               a.top_idx, a.tape, a.seed, a.gen, a.P, T,

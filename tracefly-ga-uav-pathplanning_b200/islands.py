@@ -40,6 +40,7 @@ class CudaOps:
         self.worst_set = B.SelectSet(P, n_worst) if n_worst else None
         self.side = torch.cuda.Stream() if n_worst else None
         self.reserve_sms = int(os.environ.get("TRACEFLY_RESERVE_SMS", 8))
+        self._ga_beside = self._ga_beside_src = None
 
     def fitness(self, pop):
         return self.B.fitness_batch(pop, None, self.env, self.params, want_collisions=False)[0]
@@ -49,15 +50,17 @@ class CudaOps:
 
     def generation(self, pop, fit, top, ga, seed, gen, out_pop, out_fit, beside_exchange=False):
         # while an elite exchange is in flight on the side stream, the persistent generation kernel leaves a
-        # few SMs free for it (it would otherwise hold every CTA slot until it ends)
-        if beside_exchange:
-            L.set_option(L.OPT_RESERVE_SMS, self.reserve_sms)
-        try:
-            self.B.generation(self.env, pop, fit, top, ga, self.params, seed=seed, generation=gen, out_pop=out_pop,
-                              out_fit=out_fit)
-        finally:
-            if beside_exchange:
-                L.set_option(L.OPT_RESERVE_SMS, 0)
+        # few SMs free for it (it would otherwise hold every CTA slot until it ends).  The number travels in
+        # the launch's own tf_ga_params copy: no library-wide state is touched.
+        if beside_exchange and self.reserve_sms > 0:
+            if self._ga_beside is None or self._ga_beside_src is not ga:
+                self._ga_beside = L.GaParams.from_buffer_copy(ga)
+                self._ga_beside_src = ga
+            self._ga_beside.stream_id = ga.stream_id
+            self._ga_beside.reserve_sms = self.reserve_sms
+            ga = self._ga_beside
+        self.B.generation(self.env, pop, fit, top, ga, self.params, seed=seed, generation=gen, out_pop=out_pop,
+                          out_fit=out_fit)
 
     def elites(self, fit, out):
         return self.topk_elite(fit, out=out)
@@ -112,6 +115,7 @@ class IslandGA:
         dev = pop.device
         self.top = torch.empty(self.k_rank, dtype=torch.int32, device=dev)
         self.gen = 0
+        self.hook = None
         self.migrations = 0
         self._pending = False
         if self.world > 1 and self.E > 0:
@@ -125,9 +129,15 @@ class IslandGA:
 
     # ------------------------------------------------------------------ one generation
     def step(self):
-        """rank -> select/crossover/mutate + fitness (fused); then the migration schedule."""
+        """rank -> select/crossover/mutate + fitness (fused); then the migration schedule.
+        `self.hook`, if set, is called as hook("generation_begin" | "generation_end", self) right around the
+        launch of the generation kernel (bench.py records its CUDA events there)."""
         self.ops.rank(self.fit, self.top)
+        if self.hook is not None:
+            self.hook("generation_begin", self)
         self.launch_generation()
+        if self.hook is not None:
+            self.hook("generation_end", self)
         self.pop, self.nxt = self.nxt, self.pop
         self.fit, self.nfit = self.nfit, self.fit
         self.gen += 1
