@@ -269,7 +269,7 @@ int tf_init_walks(uint64_t seed, const float* start_dev /* f32[P][4] or NULL */,
 int tf_pack_elites(const float* pop_dev, const float* fit_dev, const int32_t* elite_idx_dev, int E, int W,
                    float* rows_dev, float* rfit_dev, void* stream);
 /* gathered rows f32[world][E][W][4] / fit f32[world][E]; the j-th FOREIGN elite (source rank
- * ascending, skipping self_rank, then elite rank) overwrites pop[worst_idx[j]], fit[...].
+ * ascending, skipping self_rank, then position in its rows) overwrites pop[worst_idx[j]], fit[...].
  * worst_idx: the (world-1)*E victims, e.g. from tf_select_set(..., worst = 1). */
 int tf_replace_worst(float* pop_dev, float* fit_dev, const int32_t* worst_idx_dev, int W,
                      const float* gathered_rows_dev, const float* gathered_fit_dev,

@@ -1,9 +1,9 @@
 """Single-process CPU restatement of the island model — TEST INFRASTRUCTURE like the rest of
 oracle/: the checker of tests/test_islands_gloo.py, of the multi-GPU `-m gpu` test and of bench.py's N > 1
 correctness gate.  The reference is single-population (HR:115 keeps 2 elites), so this restatement is what
-defines the N-island behaviour: every `interval` generations each island's E best (stable rank order) are
-gathered from all islands; island r overwrites its (world - 1) * E worst — victims in ascending index order —
-with the foreign elites ordered by source rank, then elite rank.  Pipelined schedule: the elites of generation
+defines the N-island behaviour: every `interval` generations each island's E best (as a set under the stable
+order, listed by ascending index) are gathered from all islands; island r overwrites its (world - 1) * E worst — victims in ascending index order —
+with the foreign elites ordered by source rank, then elite index.  Pipelined schedule: the elites of generation
 g replace the worst of generation g + 1."""
 import numpy as np
 
@@ -35,7 +35,7 @@ def simulate(world, make_island, ga_kw, seed, gens, interval, E, pipelined, k_ra
                 insert(pending)
                 pending = None
             if (gen + 1) % interval == 0:
-                packs = [O.pack_elites(s["pop"], s["fit"], O.topk(s["fit"], E)) for s in st]
+                packs = [O.pack_elites(s["pop"], s["fit"], O.select_set(s["fit"], E, worst=False)) for s in st]
                 if pipelined:
                     pending = packs
                 else:

@@ -286,6 +286,25 @@ def test_select_set_is_the_topk_set_in_index_order(tf, P, k):
         assert np.array_equal(got, O.select_set(vals, k, worst=worst))
 
 
+def test_select_set_special_values_and_reuse(tf):
+    """One cooperative launch (round 2): all-equal fitness, +-0, +-inf, negative values, k == P, and a workspace
+    that is reused back to back (the kernel hands it back zeroed)."""
+    torch, L, B = tf
+    rng = np.random.default_rng(3)
+    P = 40_000
+    cases = [np.full(P, 0.25, np.float32),
+             np.where(rng.random(P) < 0.5, 0.0, -0.0).astype(np.float32),
+             rng.choice(np.array([-np.inf, -1.5, -0.0, 0.0, 1e-30, 2.0, np.inf], np.float32), size=P),
+             rng.standard_normal(P).astype(np.float32)]
+    for k in (1, 2, 257, 4096, P - 1, P):
+        sel = B.SelectSet(P, k)
+        for vals in cases:
+            fit = torch.from_numpy(vals).cuda()
+            for worst in (False, True, True, False):
+                got = sel(fit, worst=worst).cpu().numpy()
+                assert np.array_equal(got, O.select_set(vals, k, worst=worst)), (k, worst)
+
+
 def test_evolve_batch_resume_is_bit_identical(tf, tmp_path):
     """Checkpoint / resume: Philox is counter-based, so 12 generations == 5 + resume + 7."""
     torch, L, B = tf
@@ -308,7 +327,7 @@ def test_evolve_batch_resume_is_bit_identical(tf, tmp_path):
 
 
 def test_island_exchange_kernels_match_the_oracle(tf):
-    """The device side of an elite migration (islands.CudaOps: tf_rank_topk -> tf_pack_elites -> [all-gather] ->
+    """The device side of an elite migration (islands.CudaOps: tf_select_set -> tf_pack_elites -> [all-gather] ->
     tf_select_set -> tf_replace_worst) against the CPU restatement, with three islands emulated on one GPU (the
     all-gather is a stack); then a single-island IslandGA run against the plain rank + generation loop."""
     torch, L, B = tf
@@ -334,7 +353,7 @@ def test_island_exchange_kernels_match_the_oracle(tf):
         ops.worst(fits[r], worst)
         ops.replace(pops[r], fits[r], worst, rows, rfit, world, r, E)
     torch.cuda.synchronize()
-    packs = [O.pack_elites(ref_pop[r], ref_fit[r], O.topk(ref_fit[r], E)) for r in range(world)]
+    packs = [O.pack_elites(ref_pop[r], ref_fit[r], O.select_set(ref_fit[r], E, worst=False)) for r in range(world)]
     grows, gfit = np.stack([p[0] for p in packs]), np.stack([p[1] for p in packs])
     assert np.array_equal(grows, rows.cpu().numpy()) and np.array_equal(gfit, rfit.cpu().numpy())
     for r in range(world):

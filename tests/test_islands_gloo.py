@@ -1,7 +1,7 @@
 """Island model host logic on CPU: world_size 2 over gloo.  The device operations
 are swapped for the oracle's (tests may use the oracle; the product always uses CudaOps), so this
 checks the scheduling, the all-gather layout and the deterministic replacement order:
-the j-th foreign elite (source rank ascending, then elite rank) overwrites the j-th worst."""
+the j-th foreign elite (source rank ascending, then elite index) overwrites the j-th worst."""
 import os
 import sys
 
@@ -39,7 +39,7 @@ class OracleOps:
         out_fit.copy_(torch.from_numpy(self.O.fitness_f32(self.oenv, nxt)[0]))
 
     def elites(self, fit, out):
-        out.copy_(torch.from_numpy(self.O.topk(fit.numpy(), self.E)))
+        out.copy_(torch.from_numpy(self.O.select_set(fit.numpy(), self.E, worst=False)))
         return out
 
     def worst(self, fit, out):

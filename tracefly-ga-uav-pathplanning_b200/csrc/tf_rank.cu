@@ -327,81 +327,204 @@ static int run_select(const float* values, int P, int k, int worst, int32_t* idx
 static int run_select(const double*, int, int, int, int32_t*, void*, int64_t, cudaStream_t) { return TF_ERR_UNSUPPORTED; }
 
 // ------------------------------------------------------------------------------------------
-// The k best (or worst) chromosomes as a SET, returned in ascending index order: the same radix
-// select pins the k-th key, then an ordered compaction (per-block counts -> scan -> scatter)
-// replaces the final sort.  Used for the victims of island migration, where only a deterministic
-// assignment matters, not the rank order (k = (world-1) * E = 7168 at 8 GPUs).
-constexpr int kSetBlock = 1024;  // elements per block of the ordered compaction (256 threads x 4)
+// The k best (or worst) chromosomes as a SET, returned in ascending index order (the victims and the elites of
+// island migration, where only a deterministic assignment matters, not the rank order; k = (world-1) * E = 7168
+// victims at 8 GPUs).
+constexpr int kSetBlock = 1024;  // sizes the caller's workspace (kept from the multi-launch version: ABI-stable)
 
-__global__ void __launch_bounds__(256)
-set_count_kernel(const float* __restrict__ values, int P, int worst, const SelState* __restrict__ st,
-                 unsigned int* __restrict__ block_counts) {
-    __shared__ unsigned int total;
-    if (threadIdx.x == 0) total = 0;
-    __syncthreads();
-    const unsigned long long K = st->prefix;
-    unsigned int n = 0;
-    for (int j = 0; j < 4; ++j) {
-        const int i = blockIdx.x * kSetBlock + j * 256 + threadIdx.x;
-        if (i < P) n += Key32::make(values[i], (uint32_t)i, worst != 0).v <= K ? 1u : 0u;
-    }
-    n = __reduce_add_sync(0xffffffffu, n);
-    if ((threadIdx.x & 31) == 0 && n) atomicAdd(&total, n);
-    __syncthreads();
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+static int64_t set_workspace_bytes(int P) {
+    return 256 + 256 + (int64_t)kSelPasses * kSelBins * 4 + (int64_t)((P + kSetBlock - 1) / kSetBlock) * 4 + 256;
 }
 
-__global__ void __launch_bounds__(1024) set_scan_kernel(unsigned int* __restrict__ block_counts, int nblocks) {
-    __shared__ unsigned int part[1024];
-    const int per = (nblocks + 1023) / 1024;
-    const int lo = threadIdx.x * per, hi = min(nblocks, lo + per);
-    unsigned int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += block_counts[i];
+// ------------------------------------------------------------------------------------------
+// tf_select_set in ONE launch (round 2).  The victims of an elite exchange sit on the critical path of the island
+// model (and so do the elites, once their selection no longer competes with the generation kernel for SMs): ten
+// short launches cost ~90 us at P = 1 M although the fitness vector is 4 MB.  One cooperative kernel (every CTA
+// resident, grid barriers through a global counter) does the whole job:
+//   passes 0-2  MSD radix select on the 32-bit orderable FITNESS key h (11 + 11 + 10 bits): every CTA adds its
+//               shared-memory histogram to the global one, waits at the barrier, and scans the 2048 bins itself
+//               (no designated CTA, no second barrier) -> threshold T, the number of keys below it, the number
+//               of ties at it;
+//   pass 3      ordered compaction.  A CTA owns a contiguous chunk of the index range; counts of (h < T, h == T)
+//               per CTA -> barrier -> every CTA sums the counts of the CTAs before it -> scatter.  Ties at T are
+//               resolved by index exactly as the composite 64-bit key did: the t smallest indices for `best`,
+//               the t largest for `worst`.
+// Output: the k selected indices in ascending index order — bit-identical to the multi-launch version.
+constexpr int kOneThreads = 256;
+constexpr int kOneMaxGrid = 1024;
+struct OneCtl {
+    unsigned int arrived;      // grid barrier: monotonically increasing
+    unsigned int finished;     // CTAs that left the kernel (the last one hands the workspace back zeroed)
+    unsigned int pad[2];
+};
+__device__ __forceinline__ uint32_t sel_key32(float f, bool worst) {
+    if (f == 0.0f) f = 0.0f;  // -0.0 == +0.0 for Python's comparison
+    uint32_t u = __float_as_uint(f);
+    u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;  // ascending u <=> ascending f
+    return worst ? u : ~u;                        // the k SMALLEST keys are selected
+}
+__device__ __forceinline__ void one_barrier(OneCtl* ctl, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&ctl->arrived, 1u);
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&ctl->arrived) : "memory");
+        } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+// every CTA: digit of this level whose cumulative count reaches `need` (1-based rank inside the current prefix)
+__device__ __forceinline__ void one_pick(const unsigned int* __restrict__ hist, int nbins, unsigned int need, unsigned int* part,
+                                         unsigned int& digit, unsigned int& before_out, unsigned int& at_out) {
+    constexpr int per = kSelBins / kOneThreads;  // 8 bins per thread
+    unsigned int loc[per], sum = 0;
+#pragma unroll
+    for (int i = 0; i < per; ++i) {
+        const int bin = threadIdx.x * per + i;
+        loc[i] = bin < nbins ? __ldcg(hist + bin) : 0u;  // other CTAs' atomics: read through L2
+        sum += loc[i];
+    }
     part[threadIdx.x] = sum;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        unsigned int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+    for (int off = 1; off < kOneThreads; off <<= 1) {  // inclusive Hillis-Steele scan
+        const unsigned int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
         __syncthreads();
         part[threadIdx.x] += v;
         __syncthreads();
     }
-    unsigned int run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
-    for (int i = lo; i < hi; ++i) {  // exclusive offsets, in place
-        const unsigned int c = block_counts[i];
-        block_counts[i] = run;
-        run += c;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-set_scatter_kernel(const float* __restrict__ values, int P, int worst, int k, const SelState* __restrict__ st,
-                   const unsigned int* __restrict__ block_offsets, int32_t* __restrict__ idx) {
-    __shared__ unsigned int warp_tot[4][8];
-    const unsigned long long K = st->prefix;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    bool sel[4];
-    unsigned int mask[4];
-    for (int j = 0; j < 4; ++j) {
-        const int i = blockIdx.x * kSetBlock + j * 256 + threadIdx.x;
-        sel[j] = i < P && Key32::make(values[i], (uint32_t)i, worst != 0).v <= K;
-        mask[j] = __ballot_sync(0xffffffffu, sel[j]);
-        if (lane == 0) warp_tot[j][warp] = __popc(mask[j]);
+    const unsigned int before = threadIdx.x ? part[threadIdx.x - 1] : 0u;
+    __shared__ unsigned int res[3];
+    if (before < need && need <= part[threadIdx.x]) {
+        unsigned int run = before;
+        int i = 0;
+        for (; i < per - 1; ++i) {
+            if (run + loc[i] >= need) break;
+            run += loc[i];
+        }
+        res[0] = (unsigned int)(threadIdx.x * per + i);
+        res[1] = run;
+        res[2] = loc[i];
     }
     __syncthreads();
-    unsigned int base = block_offsets[blockIdx.x];
-    for (int j = 0; j < 4; ++j) {  // element order inside the block: j-major, then thread
-        unsigned int before = 0;
-        for (int w = 0; w < warp; ++w) before += warp_tot[j][w];
-        if (sel[j]) {
-            const unsigned int pos = base + before + __popc(mask[j] & ((1u << lane) - 1u));
-            if (pos < (unsigned int)k) idx[pos] = blockIdx.x * kSetBlock + j * 256 + threadIdx.x;
-        }
-        for (int w = 0; w < 8; ++w) base += warp_tot[j][w];
-    }
+    digit = res[0];
+    before_out = res[1];
+    at_out = res[2];
+    __syncthreads();
 }
 
-static int64_t set_workspace_bytes(int P) {
-    return 256 + 256 + (int64_t)kSelPasses * kSelBins * 4 + (int64_t)((P + kSetBlock - 1) / kSetBlock) * 4 + 256;
+__global__ void __launch_bounds__(kOneThreads)
+select_set_one_kernel(const float* __restrict__ values, int P, int k, int worst, OneCtl* ctl, unsigned int* __restrict__ hist,
+                      unsigned int* __restrict__ cta_counts, int32_t* __restrict__ idx) {
+    __shared__ unsigned int sh[kSelBins];
+    __shared__ unsigned int part[kOneThreads];
+    __shared__ unsigned int warp_tot[2][kOneThreads / 32];
+    const unsigned int G = gridDim.x;
+    const int shifts[3] = {21, 10, 0}, widths[3] = {11, 11, 10};
+    uint32_t prefix = 0;          // digits chosen so far (high bits of T)
+    unsigned int need = (unsigned int)k, n_eq = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int i = threadIdx.x; i < kSelBins; i += kOneThreads) sh[i] = 0;
+        __syncthreads();
+        const int shift = shifts[pass], width = widths[pass];
+        for (int i = blockIdx.x * kOneThreads + threadIdx.x; i < P; i += G * kOneThreads) {
+            const uint32_t h = sel_key32(values[i], worst != 0);
+            if (pass == 0 || (h >> (shift + width)) == prefix) atomicAdd(&sh[(h >> shift) & ((1u << width) - 1u)], 1u);
+        }
+        __syncthreads();
+        unsigned int* hg = hist + pass * kSelBins;
+        for (int i = threadIdx.x; i < kSelBins; i += kOneThreads)
+            if (sh[i]) atomicAdd(&hg[i], sh[i]);
+        one_barrier(ctl, (unsigned int)(pass + 1) * G);
+        unsigned int digit, before, at;
+        one_pick(hg, 1 << width, need, part, digit, before, at);
+        prefix = (prefix << width) | digit;
+        need -= before;           // rank among the keys of the chosen bin
+        n_eq = at;
+    }
+    const uint32_t T = prefix;                     // the k-th smallest key
+    const unsigned int t = need;                   // ties at T that are selected (1 <= t <= n_eq)
+    // ---- ordered compaction over contiguous chunks
+    const int chunk = ((P + (int)G - 1) / (int)G + kOneThreads - 1) / kOneThreads * kOneThreads;
+    const int lo = blockIdx.x * chunk, hi = min(P, lo + chunk);
+    unsigned int c_less = 0, c_eq = 0;
+    for (int i = lo + threadIdx.x; i < hi; i += kOneThreads) {
+        const uint32_t h = sel_key32(values[i], worst != 0);
+        c_less += h < T ? 1u : 0u;
+        c_eq += h == T ? 1u : 0u;
+    }
+    c_less = __reduce_add_sync(0xffffffffu, c_less);
+    c_eq = __reduce_add_sync(0xffffffffu, c_eq);
+    if ((threadIdx.x & 31) == 0) { warp_tot[0][threadIdx.x >> 5] = c_less; warp_tot[1][threadIdx.x >> 5] = c_eq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int a = 0, e = 0;
+        for (int w = 0; w < kOneThreads / 32; ++w) { a += warp_tot[0][w]; e += warp_tot[1][w]; }
+        cta_counts[2 * blockIdx.x] = a;
+        cta_counts[2 * blockIdx.x + 1] = e;
+    }
+    one_barrier(ctl, 4u * G);
+    unsigned int less_before = 0, eq_before = 0;
+    for (unsigned int b = threadIdx.x; b < blockIdx.x; b += kOneThreads) {
+        less_before += __ldcg(cta_counts + 2 * b);
+        eq_before += __ldcg(cta_counts + 2 * b + 1);
+    }
+    __syncthreads();
+    part[threadIdx.x] = less_before;
+    sh[threadIdx.x] = eq_before;
+    __syncthreads();
+    for (int off = kOneThreads / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) { part[threadIdx.x] += part[threadIdx.x + off]; sh[threadIdx.x] += sh[threadIdx.x + off]; }
+        __syncthreads();
+    }
+    less_before = part[0];
+    eq_before = sh[0];
+    __syncthreads();
+    // ties: `best` keeps eq ranks [0, t), `worst` keeps [n_eq - t, n_eq)  (ranks in ascending index order)
+    const unsigned int eq_lo = worst ? n_eq - t : 0u, eq_hi = worst ? n_eq : t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = lo; base < hi; base += kOneThreads) {
+        const int i = base + threadIdx.x;
+        bool is_less = false, is_eq = false;
+        if (i < hi) {
+            const uint32_t h = sel_key32(values[i], worst != 0);
+            is_less = h < T;
+            is_eq = h == T;
+        }
+        const unsigned int m_less = __ballot_sync(0xffffffffu, is_less), m_eq = __ballot_sync(0xffffffffu, is_eq);
+        if (lane == 0) { warp_tot[0][warp] = __popc(m_less); warp_tot[1][warp] = __popc(m_eq); }
+        __syncthreads();
+        unsigned int lb = less_before, eb = eq_before, tl = 0, te = 0;
+        for (int w = 0; w < kOneThreads / 32; ++w) {
+            if (w < warp) { lb += warp_tot[0][w]; eb += warp_tot[1][w]; }
+            tl += warp_tot[0][w];
+            te += warp_tot[1][w];
+        }
+        lb += __popc(m_less & ((1u << lane) - 1u));
+        eb += __popc(m_eq & ((1u << lane) - 1u));
+        // selected ties before this element: |[eq_lo, eq_hi) ∩ [0, eb)|
+        const unsigned int sel_eq_before = eb <= eq_lo ? 0u : (eb < eq_hi ? eb - eq_lo : eq_hi - eq_lo);
+        if (is_less || (is_eq && eb >= eq_lo && eb < eq_hi)) {
+            const unsigned int pos = lb + sel_eq_before;
+            if (pos < (unsigned int)k) idx[pos] = i;
+        }
+        less_before += tl;
+        eq_before += te;
+        __syncthreads();
+    }
+    // the last CTA to leave hands the workspace back zeroed (all CTAs are past their last read of it)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        part[0] = atomicAdd(&ctl->finished, 1u) == G - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (part[0]) {
+        for (int i = threadIdx.x; i < 3 * kSelBins; i += kOneThreads) hist[i] = 0;
+        if (threadIdx.x == 0) { ctl->arrived = 0; ctl->finished = 0; }
+    }
 }
 
 static int run_select_set(const float* values, int P, int k, int worst, int32_t* idx, void* ws, int64_t ws_bytes,
@@ -412,22 +535,22 @@ static int run_select_set(const float* values, int P, int k, int worst, int32_t*
     int rc = ensure_device();
     if (rc != TF_OK) return rc;
     char* base = reinterpret_cast<char*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-    SelState* state = reinterpret_cast<SelState*>(base);
+    OneCtl* ctl = reinterpret_cast<OneCtl*>(base);
     unsigned int* hist = reinterpret_cast<unsigned int*>(base + 256);
-    unsigned int* counts = reinterpret_cast<unsigned int*>(base + 256 + kSelPasses * kSelBins * 4);
-    sel_init_kernel<<<1, 256, 0, st>>>(state, hist, k);
-    TF_LAUNCH_CHECK();
-    const int grid = min((P + 255) / 256, sm_count() * 8);
-    for (int pass = 0; pass < kSelPasses; ++pass) {
-        sel_hist_kernel<<<grid, 256, 0, st>>>(values, P, worst, pass, state, hist);
-        TF_LAUNCH_CHECK();
+    unsigned int* counts = reinterpret_cast<unsigned int*>(base + 256 + 3 * kSelBins * 4);   // 2 x grid words <= 8 KB
+    // control block + histograms zeroed on the stream: the kernel also hands them back zeroed, but the caller's
+    // workspace is uninitialised memory the first time and after an aborted launch
+    TF_CUDA(cudaMemsetAsync(base, 0, 256 + 3 * kSelBins * 4, st));
+    static int occ_cache = 0;
+    int occ = __atomic_load_n(&occ_cache, __ATOMIC_RELAXED);
+    if (occ <= 0) {
+        TF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, select_set_one_kernel, kOneThreads, 0));
+        __atomic_store_n(&occ_cache, occ, __ATOMIC_RELAXED);
     }
-    const int nblocks = (P + kSetBlock - 1) / kSetBlock;
-    set_count_kernel<<<nblocks, 256, 0, st>>>(values, P, worst, state, counts);
-    TF_LAUNCH_CHECK();
-    set_scan_kernel<<<1, 1024, 0, st>>>(counts, nblocks);
-    TF_LAUNCH_CHECK();
-    set_scatter_kernel<<<nblocks, 256, 0, st>>>(values, P, worst, k, state, counts, idx);
+    // two CTAs per SM keep the barriers cheap; never more than can be resident (cooperative launch)
+    int grid = min(min(2, max(occ, 1)) * sm_count(), min(kOneMaxGrid, (P + kOneThreads - 1) / kOneThreads));
+    void* args[] = {(void*)&values, (void*)&P, (void*)&k, (void*)&worst, (void*)&ctl, (void*)&hist, (void*)&counts, (void*)&idx};
+    TF_CUDA(cudaLaunchCooperativeKernel((const void*)select_set_one_kernel, dim3(grid), dim3(kOneThreads), args, 0, st));
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

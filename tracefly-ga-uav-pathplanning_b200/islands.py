@@ -1,20 +1,23 @@
 """Island-model GA (BASELINE configs[4]): the population is split into islands,
 one per GPU / process; islands evolve independently and exchange only their elites — an NCCL
 all-gather over NVLink every `interval` generations.  Each island then overwrites its worst
-(world-1)*E chromosomes with the foreign elites (source rank ascending, then elite rank; victims
+(world-1)*E chromosomes with the foreign elites (source rank ascending, then elite index; victims
 taken in ascending index order).
 
-Pipelined migration: the elites of generation g are selected, packed and all-gathered on a SIDE
-stream while the main stream already computes generation g+1; they replace the worst of generation
-g+1 as soon as it exists.  Only the victim selection and the replace kernel stay on the critical
-path.  The schedule is deterministic (it does not depend on timing), and a synchronous `migrate()`
-is kept for warm-up / final flush.
+Pipelined migration: the elites of generation g (the E best as a set, ascending index order) are
+selected and packed on the main stream (one tf_select_set launch + one pack kernel, ~40 us at 1 M
+chromosomes), all-gathered on a SIDE stream while the main stream already computes generation g+1,
+and they replace the worst of generation g+1 as soon as it exists (tf_select_set + tf_replace_worst).
+Round 1 also ran the elite selection on the side stream: it then shared the SMs with the persistent
+generation kernel, finished late, and the step that applied the exchange waited 180-370 us for it
+(profiles/README.md, round 2).  The schedule is deterministic (it does not depend on timing), and a
+synchronous `migrate()` is kept for warm-up / final flush.
 
 The reference is single-population (HR:115 keeps 2 elites), so there is no reference behaviour
 to match here: a 1-island run is exactly `evolve_batch`, and the N-island exchange is checked
 against the CPU restatement (tests/test_islands_gloo.py, world_size 2 on gloo).
 
-The data path never touches the host: tf_rank_topk -> tf_pack_elites -> all_gather_into_tensor ->
+The data path never touches the host: tf_select_set -> tf_pack_elites -> all_gather_into_tensor ->
 tf_select_set -> tf_replace_worst.  `ops` abstracts the device operations so the same scheduling
 logic runs on CPU tensors under gloo in the tests (with the oracle's ops) — the product always
 uses `CudaOps`.
@@ -36,7 +39,7 @@ class CudaOps:
         self.B = B
         self.env, self.params = env, params
         self.topk_rank = B.TopK(P, k_rank)
-        self.topk_elite = B.TopK(P, E) if E else None
+        self.best_set = B.SelectSet(P, E) if E else None
         self.worst_set = B.SelectSet(P, n_worst) if n_worst else None
         self.side = torch.cuda.Stream() if n_worst else None
         self.reserve_sms = int(os.environ.get("TRACEFLY_RESERVE_SMS", 8))
@@ -63,7 +66,7 @@ class CudaOps:
                           out_fit=out_fit)
 
     def elites(self, fit, out):
-        return self.topk_elite(fit, out=out)
+        return self.best_set(fit, worst=False, out=out)
 
     def worst(self, fit, out):
         return self.worst_set(fit, worst=True, out=out)
@@ -167,10 +170,10 @@ class IslandGA:
         return self.ops.on_side_stream() if hasattr(self.ops, "on_side_stream") else contextlib.nullcontext()
 
     def _start_exchange(self):
-        """elites of the CURRENT population -> packed -> all-gathered (side stream on the GPU)."""
+        """elites of the CURRENT population -> packed (main stream) -> all-gathered (side stream on the GPU)."""
+        self.ops.elites(self.fit, self.elite_idx)
+        self.ops.pack(self.pop, self.fit, self.elite_idx, self.send_rows, self.send_fit)
         with self._side():
-            self.ops.elites(self.fit, self.elite_idx)
-            self.ops.pack(self.pop, self.fit, self.elite_idx, self.send_rows, self.send_fit)
             # output = the inputs of all ranks concatenated along dim 0 (accepted by NCCL and gloo alike)
             dist.all_gather_into_tensor(self.recv_rows.view(self.world * self.E, self.W, 4), self.send_rows, group=self.group)
             dist.all_gather_into_tensor(self.recv_fit.view(self.world * self.E), self.send_fit, group=self.group)
