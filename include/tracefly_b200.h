@@ -125,9 +125,10 @@ int64_t tf_voxel_grid_bytes(int nx, int ny, int nz);
 int tf_voxelize(int semantics, const tf_obstacle* obs_dev, int n, float safety_radius,
                 uint32_t* bricks_dev, int nx, int ny, int nz, void* stream);
 /* LiDAR point cloud f32[n][4] (x, y, z, pad) on the device -> occupancy bits: each point marks voxel
- * floor((p - origin) / voxel_size) — the assignment of downsample_lidar (lidar_compression.py:242-246),
- * which truncates toward zero: identical for every point inside the grid (non-negative offsets). */
-int tf_voxelize_points(const float* points_dev, int64_t n, const float origin[3], float voxel_size,
+ * int((p - origin) / voxel_size) — downsample_lidar's own arithmetic (lidar_compression.py:242-246: float64
+ * division, truncation toward zero; origin = 0 there); the set bits are its unique voxels.  Voxels outside the
+ * grid are dropped. */
+int tf_voxelize_points(const float* points_dev, int64_t n, const double origin[3], double voxel_size,
                        uint32_t* bricks_dev, int nx, int ny, int nz, void* stream);
 /* Linear bit grid (bit index x + nx*(y + ny*z), LSB first in u32 words) -> brick layout. */
 int tf_voxel_pack_linear(const uint32_t* linear_dev, uint32_t* bricks_dev, int nx, int ny, int nz, void* stream);
@@ -181,7 +182,8 @@ int tf_select_set(const float* fit_dev, int P, int k, int worst, int32_t* idx_de
 
 typedef enum tf_selection {
     TF_SEL_TRUNCATION = 0, /* HR:118: 2 distinct uniform picks from the sorted top n_top */
-    TF_SEL_TOURNAMENT = 1  /* extension: best of tournament_k uniform entrants, per parent */
+    TF_SEL_TOURNAMENT = 1, /* extension: best of tournament_k uniform entrants, per parent */
+    TF_SEL_TOP2 = 2        /* PF:192-194 select_parents: every pair's parents are the two best, in rank order */
 } tf_selection;
 typedef enum tf_crossover {
     TF_CX_SINGLE_POINT = 0, /* HR:85-89: cp in [1, min(L1,L2)-2]; c1 = p1[:cp]+p2[cp:], c2 = p2[:cp]+p1[cp:] */
@@ -220,6 +222,13 @@ void tf_ga_params_default(tf_ga_params* p);
 typedef struct tf_draw {
     int32_t pa, pb, cp, mp1, d1, mp2, d2, _pad;
 } tf_draw;
+
+/* The draws of HRMAGAGenerator.evolve (HR:117-120) for `generations` x `npairs` child pairs, taken from a COPY of
+ * NumPy's legacy global generator exactly as the reference takes them (host function, no GPU work):
+ * mt_key u32[624] / *mt_pos are np.random.get_state()[1:3] on entry and the state after the draws on return, so the
+ * caller can np.random.set_state() what the reference would have consumed.  n_top = min(10, P) (HR:118), W >= 3. */
+int tf_np_hr_tape(uint32_t* mt_key, int32_t* mt_pos, int generations, int npairs, int n_top, int W,
+                  double mutation_rate, tf_draw* tape_out);
 
 /* One GA step: next_pop <- elites + children.  tape_dev == NULL -> counter-based
  * Philox4x32-10 keyed by `seed`, counter (pair, generation, stream_id, call).
@@ -279,6 +288,17 @@ int tf_replace_worst(float* pop_dev, float* fit_dev, const int32_t* worst_idx_de
 /* GeneticAlgorithm.fitness_function of uav-backend/app/routers/GA_enhanced.py (GAE:20-26) for a ragged
  * population: fit_dev i32[P] = -len - #{i in [1, len-2] : path[i-1] != path[i+1]}. */
 int tf_fitness_gae(const float* pop_dev, const int32_t* lens_dev, int P, int W, int32_t* fit_dev, void* stream);
+
+/* Roulette selection of the backend GA (GAE:28-34: random.choices(population, [s / total for s in scores], k=2)),
+ * in two steps so that one O(P) pass serves every draw of a generation:
+ *   tf_roulette_cumweights  cum[i] = w_0 + ... + w_i with w_i = score_i / sum(score), accumulated LEFT TO RIGHT in
+ *                           float64 exactly like itertools.accumulate (a sequential pass by design: a parallel scan
+ *                           would round differently and could flip a bisect).  Scores and their sum are negative
+ *                           integers, so worse paths get larger weights — the reference's quirk, kept.
+ *   tf_select_roulette      idx[i] = bisect_right(cum, u[i] * (cum[P-1] + 0.0), 0, P - 1) for n uniform draws u
+ *                           (what random.choices does with each random()). */
+int tf_roulette_cumweights(const int32_t* score_dev, int P, double* cum_dev, void* stream);
+int tf_select_roulette(const double* cum_dev, int P, const double* u_dev, int n, int32_t* idx_dev, void* stream);
 
 /* ---- initial population of the shaped-obstacle GA ------------------------------ */
 /* `PathPlanner.find_path(dodge_strategy, height_variation)` ("GA_complex _PF.py":93-132) for n paths at once,

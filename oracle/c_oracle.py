@@ -210,6 +210,33 @@ def fitness_gae(pop, lens=None):
     return fit
 
 
+def roulette_cumweights(score):
+    """GAE:28-34 / random.choices: cumulative weights s / total, accumulated left to right in float64."""
+    score = np.ascontiguousarray(score, np.int32)
+    cum = np.zeros(len(score), np.float64)
+    lib().orc_roulette_cumweights(_p(score), len(score), _p(cum))
+    return cum
+
+
+def select_roulette(cum, u):
+    """bisect_right(cum, u * (cum[-1] + 0.0), 0, n - 1) for every uniform draw u."""
+    cum = np.ascontiguousarray(cum, np.float64)
+    u = np.ascontiguousarray(u, np.float64)
+    idx = np.zeros(len(u), np.int32)
+    lib().orc_select_roulette(_p(cum), len(cum), _p(u), len(u), _p(idx))
+    return idx
+
+
+def voxelize_points(pts, dims, origin=(0.0, 0.0, 0.0), voxel_size=1.0):
+    """downsample_lidar's voxel assignment (lidar_compression.py:242-246) as occupancy bits in brick layout."""
+    pts = np.ascontiguousarray(pts, np.float32)
+    nx, ny, nz = dims
+    bricks = np.zeros(voxel_words(nx, ny, nz), np.uint32)
+    o = (C.c_double * 3)(*[float(v) for v in origin])
+    lib().orc_voxelize_points(_p(pts), C.c_int64(len(pts)), o, C.c_double(float(voxel_size)), _p(bricks), nx, ny, nz)
+    return bricks
+
+
 def voxel_words(nx, ny, nz):
     return (nx // 8) * (ny // 8) * (nz // 8) * 16
 

@@ -381,7 +381,7 @@ def gen_find_path_pf(pf):
 def main():
     hr = ref_loader.load_hr()
     pf = ref_loader.load_pf()
-    which = set(sys.argv[1:]) or {"fitness", "evolve", "gae", "find_path"}
+    which = set(sys.argv[1:]) or {"fitness", "evolve", "gae", "find_path", "ops_pf", "lidar"}
     if "fitness" in which:
         gen_fitness_hr(hr)
         gen_fitness_pf(pf)
@@ -403,7 +403,103 @@ def main():
         gen_run_gae()
     if "find_path" in which:
         gen_find_path_pf(pf)
+    if "ops_pf" in which:
+        gen_ops_pf(pf)
+    if "lidar" in which:
+        gen_downsample_lidar()
 
+
+
+
+# --------------------------------------------------------------------------- PF crossover / mutate called directly
+def gen_ops_pf(pf):
+    """GeneticAlgorithm.crossover (PF:196-200) and .mutate (PF:202-208) of the unmodified reference, called
+    directly on seeded ragged parents (PF's own evolve drops its children, PF:216-218, so no evolve run can pin
+    these two operators).  Records the parents, the np.random draws consumed (as tf_draw records: crossover point,
+    gate outcome, mutated waypoint incl. endpoints, per-axis delta in {-1, +1}) and both children."""
+    rng = np.random.default_rng(77)
+    ga = pf.GeneticAlgorithm.__new__(pf.GeneticAlgorithm)          # PF:175-182 without the PathPlanner population
+    n, Wmax = 400, 24
+    lens = rng.integers(3, Wmax + 1, size=(n, 2)).astype(np.int32)
+    lens[::5, 1] = lens[::5, 0]                                     # equal lengths too
+    parents = np.zeros((n, 2, Wmax, 3), np.float64)
+    for i in range(n):
+        for k in range(2):
+            L = lens[i, k]
+            parents[i, k, :L] = np.cumsum(rng.integers(-1, 2, size=(L, 3)), axis=0) + rng.integers(0, 20, size=3)
+    rates = np.where(np.arange(n) % 3 == 0, 1.0, 0.35)
+    tape = np.zeros((n, 8), np.int32)
+    clens = np.zeros((n, 2), np.int32)
+    children = np.zeros((n, 2, Wmax, 3), np.float64)
+    valid = np.zeros(n, bool)
+    np.random.seed(123)
+    for i in range(n):
+        p1 = pf.Path([tuple(int(v) for v in w) for w in parents[i, 0, :lens[i, 0]]])
+        p2 = pf.Path([tuple(int(v) for v in w) for w in parents[i, 1, :lens[i, 1]]])
+        ga.mutation_rate = float(rates[i])
+        with Recorder() as rec:
+            c1, c2 = ga.crossover(p1, p2)
+            c1 = ga.mutate(c1)
+            c2 = ga.mutate(c2)
+        ev = iter(rec.events)
+        nm, a, k, cp = next(ev)
+        assert nm == "randint" and a == (1, len(p1.waypoints) - 1)
+        row = [0, 1, int(cp)]
+        for c in (c1, c2):
+            nm, a, k, gate = next(ev)
+            assert nm == "rand"
+            if gate < rates[i]:
+                nm, a, k, mp = next(ev)
+                assert nm == "randint" and a == (0, len(c.waypoints))
+                d = []
+                for _ in range(3):
+                    nm, a, k, v = next(ev)
+                    assert nm == "choice"
+                    d.append(int(v))
+                row += [int(mp), pack_delta(d)]
+            else:
+                row += [-1, 0]
+        assert next(ev, None) is None
+        tape[i, :7] = row
+        for k, c in enumerate((c1, c2)):
+            clens[i, k] = len(c.waypoints)
+            children[i, k, :clens[i, k]] = np.array(c.waypoints, np.float64)
+        valid[i] = True
+    meta = dict(META, ref="PF:196-208", seed=123, note="tape rows: pa=0 pb=1 (the two parents of the row), cp, mp1, d1, mp2, d2; "
+                "PF draws cp from randint(1, len(parent1) - 1): a cp beyond parent2's length is legal Python slicing")
+    np.savez_compressed(os.path.join(HERE, "ops_pf.npz"), parents=parents.astype(np.int16), lens=lens, rates=rates, tape=tape,
+                        children=children.astype(np.int16), clens=clens, valid=valid, meta=np.array(json.dumps(meta)))
+    print(f"ops_pf.npz: {int(valid.sum())} pairs, mutated children {(tape[:, 3] >= 0).sum() + (tape[:, 5] >= 0).sum()}")
+
+
+# --------------------------------------------------------------------------- LiDAR voxel down-sampling
+def gen_downsample_lidar():
+    """downsample_lidar (UAV_Navigation/data_compression/lidar_compression.py:242-246).  The file is a Colab export
+    (`!pip install` at the top) and cannot be imported, so only the source lines of that one function are exec'd —
+    unmodified — and called on seeded point clouds."""
+    path = os.path.join(ref_loader.REF_ROOT, "UAV_Navigation/data_compression/lidar_compression.py")
+    with open(path) as f:
+        lines = f.readlines()
+    start = next(i for i, l in enumerate(lines) if l.startswith("def downsample_lidar("))
+    end = next(i for i in range(start + 1, len(lines)) if lines[i].strip() and not lines[i].startswith((" ", "\t")))
+    ns = {"np": np}
+    exec(compile("".join(lines[start:end]), path, "exec"), ns)
+    fn = ns["downsample_lidar"]
+    rng = np.random.default_rng(99)
+    out = {}
+    cases = [("unit", 1.0, (0.0, 48.0)), ("half", 0.5, (0.0, 20.0)), ("third", 0.3, (0.0, 14.0)), ("negative", 1.0, (-6.0, 30.0)),
+             ("coarse", 2.5, (0.0, 100.0))]
+    for name, vs, (lo, hi) in cases:
+        pts = rng.uniform(lo, hi, size=(5000, 3)).astype(np.float32)   # float32-representable: what the device receives
+        pts[:50] = np.round(pts[:50] / vs) * vs                         # points exactly on voxel boundaries
+        pts = pts.astype(np.float32)
+        vox = fn(pts.astype(np.float64), voxel_size=vs)
+        out[f"pts_{name}"] = pts
+        out[f"vox_{name}"] = np.asarray(vox, np.float64)
+        out[f"vs_{name}"] = np.array(vs)
+    meta = dict(META, ref="lidar_compression.py:242-246", cases=[c[0] for c in cases], lines=[start + 1, end])
+    np.savez_compressed(os.path.join(HERE, "downsample_lidar.npz"), meta=np.array(json.dumps(meta)), **out)
+    print("downsample_lidar.npz:", {c[0]: len(out[f"vox_{c[0]}"]) for c in cases})
 
 
 

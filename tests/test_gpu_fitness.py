@@ -2,6 +2,9 @@
   (1) goldens recorded from the unmodified reference, and (2) the CPU oracle on seeded inputs.
 Bars: collision flags bit-exact; FP32 fitness bit-exact vs the fixed-order oracle and within
 1e-5 relative of the reference (north_star); FP64 fitness bit-identical to the reference."""
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -264,18 +267,27 @@ def test_static_index_equals_full_table_loop(tf, sem, W):
 
 
 def test_voxelize_points(tf):
-    """LiDAR points -> occupancy bits (lidar_compression.py:242-246 voxel assignment), vs numpy."""
+    """LiDAR points -> occupancy bits: downsample_lidar's own arithmetic (lidar_compression.py:242-246, float64
+    division, truncation toward zero).  CUDA == oracle on random clouds with an origin, and CUDA == the voxels the
+    UNMODIFIED reference function returned (tests/golden/downsample_lidar.npz)."""
     torch, L, B = tf
     rng = np.random.default_rng(4)
     dims, origin, vs = (64, 32, 16), (-3.0, 2.0, 0.5), 0.25
     pts = rng.uniform(-5, 15, size=(20000, 4)).astype(np.float32)
     got = as_u32(B.voxelize_points(torch.from_numpy(pts).cuda(), dims, origin, vs))
-    idx = np.floor((pts[:, :3] - np.array(origin, np.float32)) * np.float32(1.0 / vs)).astype(np.int64)
-    ok = np.all((idx >= 0) & (idx < np.array(dims)), axis=1)
-    lin = np.zeros(dims[0] * dims[1] * dims[2] // 32, np.uint32)
-    b = idx[ok, 0] + dims[0] * (idx[ok, 1] + dims[1] * idx[ok, 2])
-    np.bitwise_or.at(lin, b >> 5, (np.uint32(1) << (b & 31).astype(np.uint32)))
-    assert ok.sum() > 1000 and np.array_equal(got, O.voxel_pack_linear(lin, *dims))
+    assert np.array_equal(got, O.voxelize_points(pts, dims, origin, vs)) and int(got.any())
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "downsample_lidar.npz"))
+    dims = (64, 64, 64)
+    for case in json.loads(str(g["meta"]))["cases"]:
+        p4 = np.zeros((len(g[f"pts_{case}"]), 4), np.float32)
+        p4[:, :3] = g[f"pts_{case}"]
+        vs = float(g[f"vs_{case}"])
+        bricks = as_u32(B.voxelize_points(torch.from_numpy(p4).cuda(), dims, (0.0, 0.0, 0.0), vs))
+        assert np.array_equal(bricks, O.voxelize_points(p4, dims, (0.0, 0.0, 0.0), vs))
+        grid = np.rint(g[f"vox_{case}"] / vs).astype(np.int64)          # the reference's unique voxels
+        inside = grid[np.all((grid >= 0) & (grid < np.array(dims)), axis=1)]
+        assert all(O.voxel_test(bricks, dims, *r) for r in inside)
+        assert int(sum(bin(int(w)).count("1") for w in bricks)) == len(inside)
 
 
 def test_library_sqrt_is_correctly_rounded_for_every_float(tf):

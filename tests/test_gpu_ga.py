@@ -305,6 +305,69 @@ def test_select_set_special_values_and_reuse(tf):
                 assert np.array_equal(got, O.select_set(vals, k, worst=worst)), (k, worst)
 
 
+def test_pf_operators_replay_the_reference_tape(tf):
+    """PF GeneticAlgorithm.crossover / .mutate (PF:196-208) recorded from the unmodified reference
+    (tests/golden/ops_pf.npz): ragged parents, crossover points beyond the second parent, mutated endpoints.
+    tf_ga_step / tf_ga_step_f64 in tape mode must return the reference's children."""
+    torch, L, B = tf
+    from tests.test_oracle_ops import check_children, load_ops_pf
+    g, pop, lens, tape = load_ops_pf()
+    ga = L.default_ga_params(n_elite=0, selection=L.SEL_TOURNAMENT, mutation=L.MUT_LATTICE_PF)
+    for dtype in (torch.float64, torch.float32):
+        dpop = torch.from_numpy(pop).to("cuda", dtype)
+        fit = torch.zeros(len(pop), dtype=dtype, device="cuda")
+        nxt, nlens, sel, cp = B.ga_step(dpop, fit, torch.zeros(2, dtype=torch.int32, device="cuda"), ga,
+                                        tape=tape, lens=torch.from_numpy(lens).cuda())
+        check_children(g, nxt.double().cpu().numpy(), nlens.cpu().numpy())
+        assert np.array_equal(cp.cpu().numpy(), g["tape"][:, 2])
+        onxt, onlens, _, _ = O.ga_step(pop.astype(np.float64 if dtype == torch.float64 else np.float32), np.zeros(len(pop)),
+                                       np.zeros(2, np.int32), O.default_ga(n_elite=0, selection=1, mutation=1), tape=tape, lens=lens)
+        assert np.array_equal(onxt, nxt.cpu().numpy()) and np.array_equal(onlens, nlens.cpu().numpy())
+
+
+def test_top2_selection_mode(tf):
+    """TF_SEL_TOP2 = PF:192-194 select_parents, fused and unfused, against the oracle."""
+    torch, L, B = tf
+    rng = np.random.default_rng(8)
+    P, W = 3000, 32
+    table = random_table(rng, 30, 48, sem_pf=True)
+    env, prm = B.Environment(L.SEM_PF, table, 0.0), L.default_params(dist_zero_guard=0)
+    pop = B.init_walks(3, P, W, start=(24, 24, 24), lo=(0, 0, 0), hi=(47, 47, 47))
+    fit, _ = B.fitness_batch(pop, None, env, prm)
+    top = B.rank_topk(fit, 2)
+    ga = L.default_ga_params(n_elite=2, selection=L.SEL_TOP2, mutation=L.MUT_LATTICE_PF, mutation_rate=0.4)
+    oga = O.default_ga(n_elite=2, selection=2, mutation=1, mutation_rate=0.4)
+    onxt, _, osel, ocp = O.ga_step(pop.cpu().numpy(), fit.cpu().numpy(), top.cpu().numpy(), oga, seed=21, gen=4)
+    nxt, _, sel, cp = B.ga_step(pop, fit, top, ga, seed=21, generation=4)
+    assert np.array_equal(osel, sel.cpu().numpy()) and np.array_equal(ocp, cp.cpu().numpy())
+    assert np.array_equal(onxt, nxt.cpu().numpy())
+    fnxt, ffit, _, fsel, fcp = B.generation(env, pop, fit, top, ga, prm, seed=21, generation=4, want_parity=True)
+    assert torch.equal(fnxt, nxt) and torch.equal(fsel, sel) and torch.equal(fcp, cp)
+    assert (sel[:, 0] == top[0]).all() and (sel[:, 1] == top[1]).all()
+    bad = L.default_ga_params(selection=3)
+    with pytest.raises(ValueError):
+        B.ga_step(pop, fit, top, bad)
+
+
+@pytest.mark.parametrize("P", [2, 50, 4097])
+def test_roulette_selection_kernels(tf, P):
+    """tf_roulette_cumweights + tf_select_roulette (GAE:28-34) == the oracle == CPython's random.choices."""
+    import random
+    torch, L, B = tf
+    rng = np.random.default_rng(P)
+    score = -rng.integers(20, 300, size=P).astype(np.int32)
+    cum = B.roulette_cumweights(torch.from_numpy(score).cuda())
+    assert np.array_equal(cum.cpu().numpy(), O.roulette_cumweights(score))
+    total = int(score.sum())
+    random.seed(P)
+    st = random.getstate()
+    picks = random.choices(range(P), [int(v) / total for v in score], k=999)
+    random.setstate(st)
+    u = np.array([random.random() for _ in range(999)])
+    got = B.select_roulette(cum, torch.from_numpy(u).cuda()).cpu().numpy()
+    assert list(got) == picks and np.array_equal(got, O.select_roulette(O.roulette_cumweights(score), u))
+
+
 def test_evolve_batch_resume_is_bit_identical(tf, tmp_path):
     """Checkpoint / resume: Philox is counter-based, so 12 generations == 5 + resume + 7."""
     torch, L, B = tf

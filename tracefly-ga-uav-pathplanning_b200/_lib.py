@@ -17,7 +17,7 @@ TF_ERR_INVALID, TF_ERR_SHAPE, TF_ERR_UNSUPPORTED, TF_ERR_CUDA = -1, -2, -3, -4
 TF_ERR_NOMEM, TF_ERR_NODEVICE, TF_ERR_WORKSPACE = -5, -6, -7
 SEM_NONE, SEM_HR, SEM_PF = 0, 1, 2
 KIND_SPHERE, KIND_CUBE, KIND_CYLINDER, KIND_AABB = 0, 1, 2, 3
-SEL_TRUNCATION, SEL_TOURNAMENT = 0, 1
+SEL_TRUNCATION, SEL_TOURNAMENT, SEL_TOP2 = 0, 1, 2
 CX_SINGLE_POINT, CX_UNIFORM = 0, 1
 MUT_LATTICE, MUT_LATTICE_PF, MUT_GAUSSIAN = 0, 1, 2
 W_MAX, TOPK_MAX = 256, 8192
@@ -56,7 +56,9 @@ _SIGS = {
     "tf_env_destroy": (_i, [_vp]),
     "tf_voxel_grid_bytes": (_i64, [_i, _i, _i]),
     "tf_voxelize": (_i, [_i, _vp, _i, _f, _vp, _i, _i, _i, _vp]),
-    "tf_voxelize_points": (_i, [_vp, _i64, C.POINTER(_f), _f, _vp, _i, _i, _i, _vp]),
+    "tf_voxelize_points": (_i, [_vp, _i64, C.POINTER(_d), _d, _vp, _i, _i, _i, _vp]),
+    "tf_roulette_cumweights": (_i, [_vp, _i, _vp, _vp]),
+    "tf_select_roulette": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "tf_voxel_pack_linear": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "tf_params_default": (None, [C.POINTER(Params)]),
     "tf_ga_params_default": (None, [C.POINTER(GaParams)]),
@@ -70,6 +72,7 @@ _SIGS = {
     "tf_select_set": (_i, [_vp, _i, _i, _i, _vp, _vp, _i64, _vp]),
     "tf_ga_step": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(GaParams), _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "tf_ga_step_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(GaParams), _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "tf_np_hr_tape": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp]),
     "tf_generation": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(GaParams), C.POINTER(Params), _i, _i,
                            _vp, _vp, _vp, _vp, _vp, _vp]),
     "tf_track_best": (_i, [_vp, _vp, _i, _i, _u32, _vp, _vp, _vp, _vp]),

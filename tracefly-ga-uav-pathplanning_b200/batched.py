@@ -217,7 +217,7 @@ def voxelize_points(points, dims, origin=(0.0, 0.0, 0.0), voxel_size=1.0, out=No
     nx, ny, nz = dims
     if out is None:
         out = torch.zeros(voxel_grid_words(nx, ny, nz), dtype=torch.int32, device=points.device)
-    o = (C.c_float * 3)(*[float(v) for v in origin])
+    o = (C.c_double * 3)(*[float(v) for v in origin])
     check(lib.tf_voxelize_points(_ptr(points), points.shape[0], o, float(voxel_size), _ptr(out), nx, ny, nz, _stream()),
           "tf_voxelize_points")
     return out
@@ -275,6 +275,24 @@ def fitness_gae(pop, lens):
     if P:
         check(lib.tf_fitness_gae(_ptr(pop), _ptr(lens), P, W, _ptr(fit), _stream()), "tf_fitness_gae")
     return fit
+
+
+def roulette_cumweights(score):
+    """Cumulative roulette weights of the backend GA (GAE:28-34) for int32 scores on the device -> f64[P] cuda,
+    accumulated left to right exactly like random.choices does."""
+    _chk_tensor(score, torch.int32, "score", 1)
+    cum = torch.empty(score.numel(), dtype=torch.float64, device=score.device)
+    check(lib.tf_roulette_cumweights(_ptr(score), score.numel(), _ptr(cum), _stream()), "tf_roulette_cumweights")
+    return cum
+
+
+def select_roulette(cum, u):
+    """random.choices' pick for every uniform draw u (f64 cuda tensor): bisect_right(cum, u * total) -> i32[n]."""
+    _chk_tensor(cum, torch.float64, "cum", 1)
+    _chk_tensor(u, torch.float64, "u", 1)
+    idx = torch.empty(u.numel(), dtype=torch.int32, device=cum.device)
+    check(lib.tf_select_roulette(_ptr(cum), cum.numel(), _ptr(u), u.numel(), _ptr(idx), _stream()), "tf_select_roulette")
+    return idx
 
 
 def point_query_f64(points, env):

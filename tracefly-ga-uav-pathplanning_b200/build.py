@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 # library; tracefly_b200._lib loads such a variant when TRACEFLY_B200_LIB points at it.
 OUT_DIR = os.environ.get("TF_BUILD_DIR") or os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libtracefly_b200.so")
-SOURCES = ["tf_env.cu", "tf_fitness.cu", "tf_rank.cu", "tf_ga.cu", "tf_io.cu"]
+SOURCES = ["tf_env.cu", "tf_fitness.cu", "tf_rank.cu", "tf_ga.cu", "tf_io.cu", "tf_tape.cu"]
 HEADERS = ["tf_common.cuh", "tf_fitness_dev.cuh", "tf_ga_dev.cuh", "tf_stream_dev.cuh", "tf_stream_host.cuh",
            "tf_fitness_kernels.cuh", "tf_generation_kernels.cuh", "tf_inst.cu", "../../include/tracefly_b200.h"]
 

@@ -33,8 +33,20 @@ ga_step_kernel(const V4* __restrict__ pop, const int32_t* __restrict__ lens, con
             const V4* ra = pop + (size_t)b.first * W;
             const V4* rb = pop + (size_t)b.second * W;
             V4* dst = next + (size_t)(slot0 + c) * W;
+            // child = first[:cp] + second[cp:] (Python slicing): n1 waypoints of `first`, then `second` from index cp
+            // on — the same index k unless cp exceeds len(first), which only a PF tape can ask for (PF:197-199)
+            const int n1 = uniform ? 0 : min(b.cp, lens ? lens[b.first] : W);
             for (int k = lane, s = 0; k < W; k += 32, ++s) {
-                V4 v = from_first<NW>(b, k, s, lane) ? ra[k] : rb[k];
+                V4 v;
+                if (uniform) {
+                    v = from_first<NW>(b, k, s, lane) ? ra[k] : rb[k];
+                } else if (k < n1) {
+                    v = ra[k];
+                } else {
+                    const int si = b.cp + (k - n1);
+                    v = V4{};
+                    if (si < W) v = rb[si];
+                }
                 if (k == b.mp) {  // HR:97-98
                     v.x = v.x + (decltype(v.x))b.dx;
                     v.y = v.y + (decltype(v.y))b.dy;
@@ -54,6 +66,7 @@ static int run_ga_step(const S* pop, const int32_t* lens, const F* fit, const in
     if (ga->selection == TF_SEL_TOURNAMENT && !tape && !fit) return TF_ERR_INVALID;
     if (P < 1 || W < 1 || W > TF_W_MAX) return TF_ERR_SHAPE;
     if (ga->n_elite < 0 || ga->tournament_k < 1 || ga->tournament_k > 32) return TF_ERR_SHAPE;
+    if (ga->selection < TF_SEL_TRUNCATION || ga->selection > TF_SEL_TOP2) return TF_ERR_INVALID;
     if (ga->selection == TF_SEL_TRUNCATION && (ga->n_top < 2 || P < 2)) return TF_ERR_SHAPE;
     if (lens && ga->crossover == TF_CX_UNIFORM) return TF_ERR_UNSUPPORTED;  // uniform crossover needs fixed W
     int rc = ensure_device();
@@ -225,6 +238,7 @@ extern "C" int tf_generation(const tf_env* env, const float* pop_dev, const floa
     if (ga->selection == TF_SEL_TOURNAMENT && !tape_dev && !fit_dev) return TF_ERR_INVALID;
     if (P < 1 || W < 1 || W > TF_W_MAX) return TF_ERR_SHAPE;
     if (ga->n_elite < 0 || ga->tournament_k < 1 || ga->tournament_k > 32) return TF_ERR_SHAPE;
+    if (ga->selection < TF_SEL_TRUNCATION || ga->selection > TF_SEL_TOP2) return TF_ERR_INVALID;
     if (ga->selection == TF_SEL_TRUNCATION && (ga->n_top < 2 || P < 2)) return TF_ERR_SHAPE;
     if (env->d.n_smem > kTableCap) return TF_ERR_UNSUPPORTED;  // use tf_ga_step + tf_fitness (same results)
     if (params->samples_per_segment > 64) return TF_ERR_SHAPE;

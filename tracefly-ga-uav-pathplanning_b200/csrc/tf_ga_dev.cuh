@@ -57,8 +57,8 @@ __device__ __forceinline__ ChildPlan<NW> plan_child(int slot, int ne, const F* _
     U4 r = U4{0, 0, 0, 0};
     if (tape != nullptr) {
         const tf_draw t = tape[j];
-        ia = ga.selection == TF_SEL_TRUNCATION ? top_idx[t.pa] : t.pa;
-        ib = ga.selection == TF_SEL_TRUNCATION ? top_idx[t.pb] : t.pb;
+        ia = ga.selection != TF_SEL_TOURNAMENT ? top_idx[t.pa] : t.pa;   // truncation / top-2: ranks; tournament: indices
+        ib = ga.selection != TF_SEL_TOURNAMENT ? top_idx[t.pb] : t.pb;
         cp = t.cp;
         mp = c == 0 ? t.mp1 : t.mp2;
         const int d = c == 0 ? t.d1 : t.d2;
@@ -67,7 +67,10 @@ __device__ __forceinline__ ChildPlan<NW> plan_child(int slot, int ne, const F* _
         pl.dz = (float)(((d >> 4) & 3) - 1);
     } else {
         r = philox4x32_10(k0, k1, (uint32_t)j, gen, ga.stream_id, CALL_PAIR);
-        if (ga.selection == TF_SEL_TRUNCATION) {  // HR:118 two distinct uniform ranks of the top pool
+        if (ga.selection == TF_SEL_TOP2) {  // PF:192-194 select_parents: the two best, in rank order
+            ia = top_idx[0];
+            ib = top_idx[P > 1 ? 1 : 0];
+        } else if (ga.selection == TF_SEL_TRUNCATION) {  // HR:118 two distinct uniform ranks of the top pool
             const int n = min(ga.n_top, P);
             int a = (int)mulhi32(r.x, (uint32_t)n), b = (int)mulhi32(r.y, (uint32_t)(n - 1));
             if (b >= a) ++b;
@@ -106,7 +109,13 @@ __device__ __forceinline__ ChildPlan<NW> plan_child(int slot, int ne, const F* _
     }
     const int La = lens ? lens[ia] : W, Lb = lens ? lens[ib] : W;
     const int Lmin = min(La, Lb);
-    const int L = c == 0 ? Lb : La;  // child1 = p1[:cp] + p2[cp:] has len(p2) (HR:87-88)
+    int L = c == 0 ? Lb : La;  // child1 = p1[:cp] + p2[cp:] has len(p2) whenever cp <= min(len) (HR:86-88)
+    if (tape != nullptr) {
+        // Python slicing in general (PF:197-199 draws cp from len(parent1) alone, so it may exceed len(parent2)):
+        // child = first[:cp] + second[cp:] has min(cp, len(first)) + max(0, len(second) - cp) waypoints
+        const int Lf = c == 0 ? La : Lb, Ls = c == 0 ? Lb : La;
+        L = min(cp, Lf) + max(0, Ls - cp);
+    }
     if (tape == nullptr) {
         cp = Lmin >= 3 ? 1 + (int)mulhi32(r.z, (uint32_t)(Lmin - 2)) : Lmin;  // [1, Lmin-2] (HR:86)
         const U4 s = philox4x32_10(k0, k1, (uint32_t)j, gen, ga.stream_id, CALL_CHILD + (uint32_t)c);

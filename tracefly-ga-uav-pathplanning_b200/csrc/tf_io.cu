@@ -126,35 +126,95 @@ extern "C" int tf_fitness_gae(const float* pop_dev, const int32_t* lens_dev, int
 }
 
 // ------------------------------------------------------------------------------------------
-// LiDAR point cloud -> bit-packed occupancy: every point marks the voxel that
-// contains it, floor((p - origin) / voxel_size) — the voxel assignment of `downsample_lidar`
-// (UAV_Navigation/data_compression/lidar_compression.py:242-246), kept as occupancy bits in the
-// brick layout the fitness kernels probe.  Points outside the grid are ignored.
+// LiDAR point cloud -> bit-packed occupancy: every point marks the voxel
+// int((p - origin) / voxel_size) — float64 division, truncation toward zero: the voxel assignment of
+// `downsample_lidar` (UAV_Navigation/data_compression/lidar_compression.py:242-246, origin = 0 there), kept as
+// occupancy bits in the brick layout the fitness kernels probe; its np.unique is the set of bits.  Voxels outside
+// the grid are dropped.
 namespace tf {
-__global__ void voxelize_points_kernel(const float4* __restrict__ pts, int64_t n, float ox, float oy, float oz,
-                                       float inv_voxel, uint32_t* __restrict__ bricks, int nx, int ny, int nz) {
+__global__ void voxelize_points_kernel(const float4* __restrict__ pts, int64_t n, double ox, double oy, double oz,
+                                       double voxel, uint32_t* __restrict__ bricks, int nx, int ny, int nz) {
     const int nbx = nx >> 3, nby = ny >> 3;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 p = pts[i];
-        const int x = __float2int_rd(__fmul_rn(p.x - ox, inv_voxel)), y = __float2int_rd(__fmul_rn(p.y - oy, inv_voxel)),
-                  z = __float2int_rd(__fmul_rn(p.z - oz, inv_voxel));
-        if ((unsigned)x >= (unsigned)nx || (unsigned)y >= (unsigned)ny || (unsigned)z >= (unsigned)nz) continue;
+        const double qx = __ddiv_rn(__dsub_rn((double)p.x, ox), voxel), qy = __ddiv_rn(__dsub_rn((double)p.y, oy), voxel),
+                     qz = __ddiv_rn(__dsub_rn((double)p.z, oz), voxel);
+        if (!(fabs(qx) < 2147483648.0 && fabs(qy) < 2147483648.0 && fabs(qz) < 2147483648.0)) continue;
+        const long long x = (long long)qx, y = (long long)qy, z = (long long)qz;   // astype(int): toward zero
+        if (x < 0 || x >= nx || y < 0 || y >= ny || z < 0 || z >= nz) continue;
         const size_t brick = (size_t)(x >> 3) + (size_t)nbx * ((size_t)(y >> 3) + (size_t)nby * (size_t)(z >> 3));
         atomicOr(bricks + brick * 16 + ((z & 7) * 2 + ((y & 7) >> 2)), 1u << (((y & 3) << 3) | (x & 7)));
     }
 }
+
+// GAE:28-34 roulette: cumulative weights exactly as itertools.accumulate builds them (one thread walks the
+// population left to right in float64; the integer total is reduced by the whole block first), then one bisect per
+// uniform draw.
+__global__ void __launch_bounds__(256) roulette_cumweights_kernel(const int32_t* __restrict__ score, int P, double* __restrict__ cum) {
+    __shared__ long long part[256];
+    long long t = 0;
+    for (int i = threadIdx.x; i < P; i += 256) t += score[i];
+    part[threadIdx.x] = t;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) part[threadIdx.x] += part[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    const double total = (double)part[0];
+    double run = 0.0;
+    for (int i = 0; i < P; ++i) {
+        const double w = __ddiv_rn((double)score[i], total);
+        run = i == 0 ? w : __dadd_rn(run, w);
+        cum[i] = run;
+    }
+}
+__global__ void select_roulette_kernel(const double* __restrict__ cum, int P, const double* __restrict__ u, int n,
+                                       int32_t* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double total = __dadd_rn(cum[P - 1], 0.0);
+    const double x = __dmul_rn(u[i], total);
+    int lo = 0, hi = P - 1;
+    while (lo < hi) {  // bisect_right(cum, x, 0, P - 1)
+        const int mid = (lo + hi) >> 1;
+        if (x < cum[mid]) hi = mid; else lo = mid + 1;
+    }
+    idx[i] = lo;
+}
 }  // namespace tf
 
-extern "C" int tf_voxelize_points(const float* points_dev, int64_t n, const float origin[3], float voxel_size,
+extern "C" int tf_voxelize_points(const float* points_dev, int64_t n, const double origin[3], double voxel_size,
                                   uint32_t* bricks_dev, int nx, int ny, int nz, void* stream) {
     if (!bricks_dev || !origin || (n > 0 && !points_dev) || n < 0) return TF_ERR_INVALID;
-    if (!(voxel_size > 0.0f) || tf_voxel_grid_bytes(nx, ny, nz) < 0) return TF_ERR_SHAPE;
+    if (!(voxel_size > 0.0) || tf_voxel_grid_bytes(nx, ny, nz) < 0) return TF_ERR_SHAPE;
     int rc = ensure_device();
     if (rc != TF_OK) return rc;
     if (n == 0) return TF_OK;
     const int64_t want = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
     tf::voxelize_points_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(points_dev), n, origin[0], origin[1], origin[2], 1.0f / voxel_size, bricks_dev, nx, ny, nz);
+        reinterpret_cast<const float4*>(points_dev), n, origin[0], origin[1], origin[2], voxel_size, bricks_dev, nx, ny, nz);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+
+extern "C" int tf_roulette_cumweights(const int32_t* score_dev, int P, double* cum_dev, void* stream) {
+    if (!score_dev || !cum_dev) return TF_ERR_INVALID;
+    if (P < 1) return TF_ERR_SHAPE;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    tf::roulette_cumweights_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(score_dev, P, cum_dev);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+
+extern "C" int tf_select_roulette(const double* cum_dev, int P, const double* u_dev, int n, int32_t* idx_dev, void* stream) {
+    if (!cum_dev || (n > 0 && (!u_dev || !idx_dev))) return TF_ERR_INVALID;
+    if (P < 1 || n < 0) return TF_ERR_SHAPE;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    if (n == 0) return TF_OK;
+    tf::select_roulette_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cum_dev, P, u_dev, n, idx_dev);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

@@ -8,11 +8,15 @@ Public surface kept from uav-backend/app/routers/GA_enhanced.py (GAE) so that
     UAVPathPlanner(source, destination, environment)                        .find_path(), .dodge_obstacle()
 
 Division of labour.  Upstream scores the WHOLE population inside `selection()` once per child pair
-(GAE:28-34): P/2 * P evaluations of `fitness_function` per generation.  Here a generation is scored by
-ONE `tf_fitness_gae` launch over the ragged population (`_PopulationScorer`); roulette, splice and the
-dodge mutation are O(P) list edits that stay on the host and pull from `random` / `np.random` in
-upstream's order, which is why a run under the same seeds returns upstream's path
-(tests/test_gpu_dropin_gae.py, golden recorded from the unmodified file).
+(GAE:28-34): P/2 * P evaluations of `fitness_function` per generation, and rebuilds the P roulette weights
+every time.  Here a generation is scored by ONE `tf_fitness_gae` launch over the ragged population and its
+roulette table (cumulative weights s / total, accumulated left to right like random.choices does) by ONE
+`tf_roulette_cumweights` launch (`_PopulationScorer`); each `selection()` is then a bisect on that table with
+the two `random.random()` draws upstream would take.  Splice and the dodge mutation are O(len) list edits
+that stay on the host and pull from `random` / `np.random` in upstream's order — their draw counts depend on
+the parents just selected, so the uniforms of a whole generation cannot be drawn ahead and the device-side
+`tf_select_roulette` (same bisect, one thread per draw) serves the array API, not this loop.  A run under the
+same seeds returns upstream's path (tests/test_gpu_dropin_gae.py, golden recorded from the unmodified file).
 
 Upstream behaviour that is reproduced on purpose
   * roulette weights are score / total with both negative, so WORSE paths are favoured (GAE:30-33);
@@ -49,6 +53,20 @@ class _PopulationScorer:
         dev = B.fitness_gae(torch.from_numpy(packed).cuda(), torch.from_numpy(lengths).cuda())
         return dev.cpu().tolist()
 
+    @staticmethod
+    def scores_and_roulette(paths):
+        """(scores, cumulative roulette weights) of a generation: tf_fitness_gae + tf_roulette_cumweights."""
+        count = len(paths)
+        width = max([len(p) for p in paths] + [1])
+        packed = np.zeros((count, width, 4), np.float32)
+        lengths = np.fromiter((len(p) for p in paths), np.int32, count)
+        for row, path in zip(packed, paths):
+            if path:
+                row[:len(path), :3] = np.asarray(path, np.float32).reshape(len(path), -1)[:, :3]
+        dev = B.fitness_gae(torch.from_numpy(packed).cuda(), torch.from_numpy(lengths).cuda())
+        cum = B.roulette_cumweights(dev)
+        return dev.cpu().tolist(), cum.cpu().tolist()
+
 
 class GeneticAlgorithm:
     def __init__(self, population_size, generations, mutation_rate):
@@ -56,6 +74,7 @@ class GeneticAlgorithm:
         self.population = []
         self._world = None          # environment of the current run (for the dodge mutation)
         self._generation_scores = None
+        self._generation_cum = None
 
     # -- upstream's method names -------------------------------------------------------------
     def initialize_population(self, source, destination, environment):
@@ -66,9 +85,11 @@ class GeneticAlgorithm:
         return _PopulationScorer.scores([path])[0]
 
     def selection(self):
-        scores = self._generation_scores or _PopulationScorer.scores(self.population)
-        norm = sum(scores)
-        return random.choices(self.population, [s / norm for s in scores], k=2)
+        cum = self._generation_cum
+        if cum is None:
+            _, cum = _PopulationScorer.scores_and_roulette(self.population)
+        # random.choices(population, [s / total ...], k=2) == the same call with the accumulated weights (GAE:30-33)
+        return random.choices(self.population, cum_weights=cum, k=2)
 
     def crossover(self, parent1, parent2):
         cut = random.randint(1, min(len(parent1), len(parent2)) - 1)
@@ -82,14 +103,15 @@ class GeneticAlgorithm:
         path[where] = UAVPathPlanner(anchor, path[-1], self._world).dodge_obstacle(anchor, path[-1])
 
     def evolve(self):
-        self._generation_scores = _PopulationScorer.scores(self.population)   # 1 launch, reused by every selection()
+        # 2 launches, reused by every selection() of the generation
+        self._generation_scores, self._generation_cum = _PopulationScorer.scores_and_roulette(self.population)
         offspring = []
         for _ in range(self.population_size // 2):
             pair = self.crossover(*self.selection())
             for child in pair:
                 self.mutate(child)
             offspring += pair
-        self.population, self._generation_scores = offspring, None
+        self.population, self._generation_scores, self._generation_cum = offspring, None, None
 
     def run(self, source, destination, environment):
         self._world = environment

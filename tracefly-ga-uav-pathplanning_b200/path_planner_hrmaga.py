@@ -14,13 +14,20 @@ the device as a tape, so `np.random.seed(s); HRMAGAGenerator().evolve(...)` retu
 path as the reference does under the same seed (tests/test_dropin_hr_gpu.py checks it against
 goldens recorded from the unmodified reference).
 
+Speed: the draws of a block of generations are produced natively (tf_np_hr_tape restates NumPy's legacy MT19937
+methods bit for bit and is checked against np.random before use) and the generations of a block replay as one CUDA
+graph, so BASELINE configs[0] (100 paths, 200 generations) takes milliseconds instead of the reference's 30-50 s.
+
 Deliberate, documented deviations:
   * returned waypoints are tuples of plain Python numbers (int when every input was integral,
     else float).  The reference returns NumPy scalars after the first tuple, which makes its
     own json.dump (HR:154) raise TypeError on integer inputs.
+  * a segment longer than TF_W_MAX - 1 = 255 lattice steps raises ValueError (the reference would plan it; main.py
+    plans 5-unit segments, MAIN:43-56).  A population of one path returns that path, as the reference does.
   * generate_local_path is ALSO a method of HRMAGAGenerator, because UAV_Navigation/main.py:59
     calls it as one (the reference only defines the module function, HR:138).
 """
+import ctypes as C
 import json
 import os
 from datetime import datetime
@@ -31,6 +38,40 @@ import torch
 
 from . import _lib as L
 from . import batched as B
+
+
+_NATIVE_TAPE = None
+
+
+def _native_tape_ok():
+    """True when tf_np_hr_tape reproduces np.random's legacy generator on a probe (40 generations x 7 pairs, all
+    four draw kinds, from a scratch RandomState): guards against a NumPy whose legacy streams differ from the
+    restated ones (2.3.x).  Checked once per process; the global generator is not touched."""
+    global _NATIVE_TAPE
+    if _NATIVE_TAPE is None:
+        try:
+            rs = np.random.RandomState(20240229)
+            st = rs.get_state()
+            key = np.ascontiguousarray(st[1], np.uint32).copy()
+            pos = C.c_int32(int(st[2]))
+            got = np.zeros((40, 7, 8), np.int32)
+            rc = L.lib.tf_np_hr_tape(key.ctypes.data_as(C.c_void_p), C.byref(pos), 40, 7, 6, 9, 0.4, got.ctypes.data_as(C.c_void_p))
+            want = np.zeros_like(got)
+            for g in range(40):
+                for j in range(7):
+                    pa, pb = rs.choice(6, 2, replace=False)
+                    row = [pa, pb, rs.randint(1, 8), -1, 0, -1, 0, 0]
+                    for c in range(2):
+                        if rs.rand() < 0.4:
+                            row[3 + 2 * c] = rs.randint(1, 8)
+                            d = rs.choice([-1, 0, 1], 3)
+                            row[4 + 2 * c] = int((d[0] + 1) | ((d[1] + 1) << 2) | ((d[2] + 1) << 4))
+                    want[g, j] = row
+            after = rs.get_state()
+            _NATIVE_TAPE = bool(rc == 0 and np.array_equal(got, want) and np.array_equal(after[1], key) and int(after[2]) == pos.value)
+        except Exception:
+            _NATIVE_TAPE = False
+    return _NATIVE_TAPE
 
 
 def load_obstacles_from_json(filepath: str) -> List[dict]:
@@ -156,44 +197,122 @@ class HRMAGAGenerator:
                     row[4 + 2 * c] = int((d[0] + 1) | ((d[1] + 1) << 2) | ((d[2] + 1) << 4))
             out[j] = row
 
+    def _draw_block(self, P, W, out):
+        """The draws of out.shape[0] consecutive generations into out[g, :npairs] (int32 [g, npairs, 8]), consuming
+        np.random's global generator exactly as the reference does.  Fast path: the native restatement of NumPy's
+        legacy generator (tf_np_hr_tape, ~1 us per child pair) advances a copy of the state, which is then
+        installed with np.random.set_state; used only after it has reproduced np.random itself on a probe."""
+        n_top = min(10, P)
+        G, npairs = out.shape[0], out.shape[1]
+        if npairs and W >= 3 and n_top >= 2 and _native_tape_ok():
+            st = np.random.get_state()
+            key = np.ascontiguousarray(st[1], np.uint32).copy()
+            pos = C.c_int32(int(st[2]))
+            L.check(L.lib.tf_np_hr_tape(key.ctypes.data_as(C.c_void_p), C.byref(pos), G, npairs, n_top, W,
+                                        float(self.mutation_rate), out.ctypes.data_as(C.c_void_p)), "tf_np_hr_tape")
+            np.random.set_state((st[0], key, pos.value, st[3], st[4]))
+            return
+        for g in range(G):
+            self._draw_generation(P, W, out[g])
+
     # ---- HR:101-130
     def evolve(self, start, end, obstacles):
         P = self.population_size
         env = obstacles if isinstance(obstacles, B.Environment) else _env_for(obstacles)
         pop, W = B.init_diagonal(start, end, P, f64=True)             # HR:102
+        if W > L.W_MAX:
+            raise ValueError(f"start and end are {W - 1} lattice steps apart; this drop-in plans segments of at most "
+                             f"{L.W_MAX - 1} steps (TF_W_MAX waypoints per chromosome) — split the segment as main.py does")
         params = L.default_params(dist_zero_guard=1)
         fit, _ = B.fitness_batch_f64(pop, None, env, params)          # HR:103-104
-        ga = L.default_ga_params(n_elite=2, n_top=10, selection=L.SEL_TRUNCATION, mutation_rate=self.mutation_rate)
-        ne = min(2, P)
-        npairs = (P - ne + 1) // 2
-        k = min(10, P)
-        topk = B.TopK(P, k, f64=True)
-        tracker = B.BestTracker(W, f64=True)                          # HR:106-107
-        nxt, nfit = torch.empty_like(pop), torch.empty_like(fit)
-        top = torch.empty(k, dtype=torch.int32, device="cuda")
         G = self.generations
-        tape_host = torch.zeros((max(G, 1), max(npairs, 1), 8), dtype=torch.int32).pin_memory()
-        tape_dev = torch.empty_like(tape_host, device="cuda")
-        tape_np = tape_host.numpy()
-        for gen in range(G):
-            if self.emergency_stop:                                   # HR:110-112
+        tracker = B.BestTracker(W, f64=True)                          # HR:106-107
+        if P < 2:
+            # one path: no parents to pick (HR:117 never runs), every generation re-evaluates the same path and the
+            # first one records it as best (HR:126-128); tf_ga_step needs two ranked parents, so this stays here
+            for gen in range(G):
+                if self.emergency_stop:
+                    print("[⚠️ EMERGENCY HALT TRIGGERED] Path planning interrupted.")
+                    return []
+                tracker.update(pop, fit, 0, gen)
+        else:
+            halted = self._evolve_device(pop, fit, env, params, tracker, P, W, G)
+            if halted:
                 print("[⚠️ EMERGENCY HALT TRIGGERED] Path planning interrupted.")
                 return []
-            if npairs:
-                self._draw_generation(P, W, tape_np[gen, :npairs])
-                tape_dev[gen].copy_(tape_host[gen], non_blocking=True)
-            topk(fit, out=top)                                        # HR:114
-            B.ga_step(pop, fit, top, ga, tape=tape_dev[gen], out=nxt, want_parity=False)   # HR:115-122
-            B.fitness_batch_f64(nxt, None, env, params, out=nfit, want_collisions=False)  # HR:123-124
-            pop, nxt = nxt, pop
-            fit, nfit = nfit, fit
-            tracker.update(pop, fit, 0, gen)                          # HR:126-128
         if G == 0:
             # HR:130 dereferences best_path = None when the loop never ran
             raise AttributeError("'NoneType' object has no attribute 'waypoints'")
         rows = tracker.best_path.cpu().numpy()
         path = _pythonize(rows, _is_integral(start, end))
         return path
+
+    def _evolve_device(self, pop, fit, env, params, tracker, P, W, G):
+        """HR:109-128 on the device.  The draws never depend on fitness (only on P, W and the mutation rate), so they
+        are produced a block of K generations ahead; the K generations of a block — 4 kernels each: rank, select /
+        crossover / mutate, fitness, best tracking — are captured once in a CUDA graph and replayed per block, so the
+        loop is no longer bound by Python + launch latency (BASELINE configs[0]: 802 launches, 0.104 s -> 4 eager
+        generations + 13 graph replays).  The emergency flag (HR:110-112) is polled before every block, i.e. within
+        K <= 16 generations; the np.random state is then rewound to what the generations actually run consumed.
+        Returns True when halted."""
+        ga = L.default_ga_params(n_elite=2, n_top=10, selection=L.SEL_TRUNCATION, mutation_rate=self.mutation_rate)
+        ne = min(2, P)
+        npairs = (P - ne + 1) // 2
+        k = min(10, P)
+        topk = B.TopK(P, k, f64=True)
+        nxt, nfit = torch.empty_like(pop), torch.empty_like(fit)
+        top = torch.empty(k, dtype=torch.int32, device="cuda")
+        # block size: even (the ping-pong ends where it started), <= 16, and a tape block of at most 16 MB
+        K = max(1, min(16, G, (16 << 20) // max(1, npairs * 32)))
+        K = K - (K & 1) if K > 1 else 1
+        rows = max(npairs, 1)
+        tape_host = [torch.zeros((K, rows, 8), dtype=torch.int32).pin_memory() for _ in range(2)]
+        host_free = [None, None]
+        tape_dev = torch.empty((K, rows, 8), dtype=torch.int32, device="cuda")
+        state = {"pop": pop, "nxt": nxt, "fit": fit, "nfit": nfit}
+
+        def generation(i):                                            # reads tape_dev[i]
+            topk(state["fit"], out=top)                                                                   # HR:114
+            B.ga_step(state["pop"], state["fit"], top, ga, tape=tape_dev[i], out=state["nxt"], want_parity=False)   # HR:115-122
+            B.fitness_batch_f64(state["nxt"], None, env, params, out=state["nfit"], want_collisions=False)  # HR:123-124
+            state["pop"], state["nxt"] = state["nxt"], state["pop"]
+            state["fit"], state["nfit"] = state["nfit"], state["fit"]
+            tracker.update(state["pop"], state["fit"], 0, 0)          # HR:126-128
+
+        rng0 = np.random.get_state()
+        graph, done, block = None, 0, 0
+        use_graph = K >= 2 and G >= 3 * K and os.environ.get("TRACEFLY_HR_GRAPH", "1") != "0"
+        while done < G:
+            if self.emergency_stop:                                   # HR:110-112
+                if npairs:   # the reference would have drawn for `done` generations only
+                    np.random.set_state(rng0)
+                    scratch = np.zeros((done, npairs, 8), np.int32)
+                    self._draw_block(P, W, scratch)
+                return True
+            n = min(K, G - done)
+            hb = block & 1
+            if host_free[hb] is not None:
+                host_free[hb].synchronize()                           # the H2D copy that read this buffer has finished
+            if npairs:
+                self._draw_block(P, W, tape_host[hb].numpy()[:n, :npairs])
+                tape_dev[:n].copy_(tape_host[hb][:n], non_blocking=True)
+                host_free[hb] = torch.cuda.Event()
+                host_free[hb].record()
+            if use_graph and n == K and block >= 1:
+                if graph is None:                                     # block 0 ran eagerly: every kernel is loaded
+                    graph = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(graph):
+                        for i in range(K):
+                            generation(i)
+                graph.replay()
+            else:
+                for i in range(n):
+                    generation(i)
+            done += n
+            block += 1
+        torch.cuda.current_stream().synchronize()
+        return False
 
     def emergency_halt(self):  # HR:132-133
         self.emergency_stop = True
