@@ -325,6 +325,17 @@ int tf_unpack_xyz(const float* in_dev, float* pop_dev, int64_t n_waypoints, void
 int tf_pack_xyz(const float* pop_dev, float* out_dev, int64_t n_waypoints, void* stream);
 int tf_pack_i16(const float* pop_dev, int16_t* out_dev, int64_t n_waypoints, void* stream);
 
+/* Lossy front ends of the reference's waypoint compression (UAV_Navigation/data_compression/
+ * ga_waypoints_compression.py), applied per path to paths64_dev f64[n_paths][W][4] (what tf_track_best_f64 keeps; use
+ * f32 = 1 for f32[n_paths][W][4] populations, widened to float64 first) — entropy coding (zlib / LZMA) stays on the host:
+ *   TF_CODEC_QUANT_F32   compress_waypoints (:2090-2093): np.round(w / q) * q as float32; param = q (0.05)
+ *                        out_dev f32[n_paths][W][3]   (host: zlib.compress(out.tobytes()) == the reference's bytes)
+ *   TF_CODEC_DELTA_ROUND delta_encode + quantize (:875-884): np.round(np.diff(w, axis=0, prepend=w[:1]), d);
+ *                        param = d decimals (3)       out_dev f64[n_paths][W][3]   (host: struct.pack + lzma) */
+enum { TF_CODEC_QUANT_F32 = 0, TF_CODEC_DELTA_ROUND = 1 };
+int tf_encode_waypoints(const void* paths_dev, int f32, int64_t n_paths, int W, int mode, double param, void* out_dev,
+                        void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------ */
 int tf_version(void);
 const char* tf_strerror(int status);

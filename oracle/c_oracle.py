@@ -237,6 +237,16 @@ def voxelize_points(pts, dims, origin=(0.0, 0.0, 0.0), voxel_size=1.0):
     return bricks
 
 
+def encode_waypoints(paths, mode, param):
+    """paths f64[n, W, 4] -> mode 0: f32[n, W, 3] quantised to a `param` grid (ga_waypoints_compression.py:2090-2093);
+    mode 1: f64[n, W, 3] deltas rounded to `param` decimals (:875-884)."""
+    paths = np.ascontiguousarray(paths, np.float64)
+    n, W, _ = paths.shape
+    out = np.zeros((n, W, 3), np.float32 if mode == 0 else np.float64)
+    lib().orc_encode_waypoints(_p(paths), C.c_int64(n), W, int(mode), C.c_double(float(param)), _p(out))
+    return out
+
+
 def voxel_words(nx, ny, nz):
     return (nx // 8) * (ny // 8) * (nz // 8) * 16
 

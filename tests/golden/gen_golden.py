@@ -381,7 +381,7 @@ def gen_find_path_pf(pf):
 def main():
     hr = ref_loader.load_hr()
     pf = ref_loader.load_pf()
-    which = set(sys.argv[1:]) or {"fitness", "evolve", "gae", "find_path", "ops_pf", "lidar"}
+    which = set(sys.argv[1:]) or {"fitness", "evolve", "gae", "find_path", "ops_pf", "lidar", "codecs"}
     if "fitness" in which:
         gen_fitness_hr(hr)
         gen_fitness_pf(pf)
@@ -407,6 +407,8 @@ def main():
         gen_ops_pf(pf)
     if "lidar" in which:
         gen_downsample_lidar()
+    if "codecs" in which:
+        gen_waypoint_codecs()
 
 
 
@@ -500,6 +502,47 @@ def gen_downsample_lidar():
     meta = dict(META, ref="lidar_compression.py:242-246", cases=[c[0] for c in cases], lines=[start + 1, end])
     np.savez_compressed(os.path.join(HERE, "downsample_lidar.npz"), meta=np.array(json.dumps(meta)), **out)
     print("downsample_lidar.npz:", {c[0]: len(out[f"vox_{c[0]}"]) for c in cases})
+
+
+
+# --------------------------------------------------------------------------- waypoint egress codecs
+def _exec_functions(path, names, ns):
+    """exec the source lines of top-level functions of a Colab export that cannot be imported.  names: (name, line)
+    pairs — the file redefines some names several times; `line` (1-based) picks the definition."""
+    with open(path) as f:
+        lines = f.readlines()
+    for name, line in names:
+        start = line - 1
+        assert lines[start].startswith(f"def {name}("), lines[start]
+        end = next(i for i in range(start + 1, len(lines)) if lines[i].strip() and not lines[i].startswith((" ", "\t")))
+        exec(compile("".join(lines[start:end]), path, "exec"), ns)
+    return ns
+
+
+def gen_waypoint_codecs():
+    """The two lossy front ends the reference puts before its entropy coders
+    (UAV_Navigation/data_compression/ga_waypoints_compression.py): compress_waypoints (:2090-2094, quantise to a
+    0.05 grid -> float32 -> zlib) and delta_encode + quantize (:875-885, np.diff with a zero first row, rounded to 3
+    decimals, packed as doubles), run UNMODIFIED on seeded routes (the file's own generate_route recipe, :2086-2087)
+    and on lattice GA paths."""
+    import zlib
+    path = os.path.join(ref_loader.REF_ROOT, "UAV_Navigation/data_compression/ga_waypoints_compression.py")
+    ns = _exec_functions(path, [("compress_waypoints", 2090), ("delta_encode", 875), ("quantize", 882)], {"np": np, "zlib": zlib})
+    rng = np.random.default_rng(31)
+    routes = {"route": np.cumsum(rng.standard_normal((300, 3)) * 10, axis=0),
+              "lattice": np.cumsum(rng.integers(-1, 2, size=(64, 3)), axis=0).astype(np.float64) + 500.0,
+              "ties": (rng.integers(-40, 40, size=(200, 3)) * 0.025),          # exact halves of the 0.05 grid
+              "short": np.array([[1.0, 2.0, 3.0]])}
+    out = {}
+    for name, w in routes.items():
+        comp = ns["compress_waypoints"](w, 0.05)
+        out[f"in_{name}"] = w
+        out[f"q32_{name}"] = np.frombuffer(zlib.decompress(comp), dtype=np.float32).reshape(w.shape)
+        out[f"zlib_{name}"] = np.frombuffer(comp, dtype=np.uint8)
+        out[f"dq_{name}"] = ns["quantize"](ns["delta_encode"](w))
+    meta = dict(META, ref="ga_waypoints_compression.py:875-885,2090-2094", cases=list(routes), zlib=zlib.ZLIB_VERSION)
+    np.savez_compressed(os.path.join(HERE, "waypoint_codecs.npz"), meta=np.array(json.dumps(meta)), **out)
+    print("waypoint_codecs.npz:", {k: v.shape for k, v in routes.items()})
 
 
 

@@ -368,6 +368,32 @@ def test_roulette_selection_kernels(tf, P):
     assert list(got) == picks and np.array_equal(got, O.select_roulette(O.roulette_cumweights(score), u))
 
 
+def test_waypoint_codecs_on_device(tf):
+    """tf_encode_waypoints == the unmodified reference functions (tests/golden/waypoint_codecs.npz) == the oracle, from
+    float64 paths and from a float32 population; the host-side zlib of the device bytes is the reference's stream."""
+    import json
+    import os
+    import zlib
+    torch, L, B = tf
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "waypoint_codecs.npz"))
+    for case in json.loads(str(g["meta"]))["cases"]:
+        w = g[f"in_{case}"]
+        p4 = np.zeros((1, len(w), 4))
+        p4[0, :, :3] = w
+        q = B.encode_waypoints(torch.from_numpy(p4).cuda(), L.CODEC_QUANT_F32, 0.05).cpu().numpy()[0]
+        assert np.array_equal(q.view(np.uint32), g[f"q32_{case}"].view(np.uint32)), case
+        if json.loads(str(g["meta"]))["zlib"] == zlib.ZLIB_VERSION:
+            assert np.array_equal(np.frombuffer(zlib.compress(q.tobytes()), np.uint8), g[f"zlib_{case}"])
+        d = B.encode_waypoints(torch.from_numpy(p4).cuda(), L.CODEC_DELTA_ROUND, 3).cpu().numpy()[0]
+        assert np.array_equal(d.view(np.uint64), g[f"dq_{case}"].view(np.uint64)), case
+    pop = B.init_walks(2, 500, 64, start=(100, 100, 100), lo=(0, 0, 0), hi=(1023, 1023, 1023))
+    for mode, prm in ((L.CODEC_QUANT_F32, 0.05), (L.CODEC_DELTA_ROUND, 3)):
+        got = B.encode_waypoints(pop, mode, prm).cpu().numpy()
+        assert np.array_equal(got, O.encode_waypoints(pop.cpu().numpy().astype(np.float64), mode, prm))
+    with pytest.raises(ValueError):
+        B.encode_waypoints(pop, L.CODEC_QUANT_F32, 0.0)
+
+
 def test_evolve_batch_resume_is_bit_identical(tf, tmp_path):
     """Checkpoint / resume: Philox is counter-based, so 12 generations == 5 + resume + 7."""
     torch, L, B = tf

@@ -113,3 +113,20 @@ def test_roulette_is_random_choices(P, seed):
     assert list(O.select_roulette(cum, u)) == picks
     # the quirk: the WORST score carries the largest weight
     assert int(np.argmax(np.diff(np.concatenate([[0.0], cum])))) == int(np.argmin(score))
+
+
+@pytest.mark.parametrize("case", ["route", "lattice", "ties", "short"])
+def test_waypoint_codecs_vs_reference(case):
+    """orc_encode_waypoints == compress_waypoints' quantiser (ga_waypoints_compression.py:2090-2093; the zlib stream
+    of our bytes is the reference's stream) and == delta_encode + quantize (:875-884), bit for bit."""
+    import zlib
+    g = np.load(os.path.join(GOLD, "waypoint_codecs.npz"))
+    w = g[f"in_{case}"]
+    p4 = np.zeros((1, len(w), 4))
+    p4[0, :, :3] = w
+    q = O.encode_waypoints(p4, 0, 0.05)[0]
+    assert np.array_equal(q.view(np.uint32), g[f"q32_{case}"].view(np.uint32))
+    if json.loads(str(g["meta"]))["zlib"] == zlib.ZLIB_VERSION:
+        assert np.array_equal(np.frombuffer(zlib.compress(q.tobytes()), np.uint8), g[f"zlib_{case}"])
+    d = O.encode_waypoints(p4, 1, 3)[0]
+    assert np.array_equal(d.view(np.uint64), g[f"dq_{case}"].view(np.uint64))

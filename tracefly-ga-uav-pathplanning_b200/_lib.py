@@ -57,6 +57,7 @@ _SIGS = {
     "tf_voxel_grid_bytes": (_i64, [_i, _i, _i]),
     "tf_voxelize": (_i, [_i, _vp, _i, _f, _vp, _i, _i, _i, _vp]),
     "tf_voxelize_points": (_i, [_vp, _i64, C.POINTER(_d), _d, _vp, _i, _i, _i, _vp]),
+    "tf_encode_waypoints": (_i, [_vp, _i, _i64, _i, _i, _d, _vp, _vp]),
     "tf_roulette_cumweights": (_i, [_vp, _i, _vp, _vp]),
     "tf_select_roulette": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "tf_voxel_pack_linear": (_i, [_vp, _vp, _i, _i, _i, _vp]),
@@ -144,6 +145,7 @@ def philox(key0, key1, c0, c1, c2, c3):
     return [int(v) for v in out]
 
 
+CODEC_QUANT_F32, CODEC_DELTA_ROUND = 0, 1
 DODGE = {"up": 0, "down": 1, "left": 2, "right": 3, "forward": 4, "backward": 5}
 OPT_DISABLE_STREAM = 1
 OPT_STREAM_SCHEDULE = 2

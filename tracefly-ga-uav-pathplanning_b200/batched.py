@@ -552,6 +552,27 @@ def checkpoint(result, path=None):
     return state
 
 
+# ------------------------------------------------------------------------------------ result egress
+def encode_waypoints(paths, mode=L.CODEC_QUANT_F32, param=None):
+    """The lossy front ends of the reference's waypoint compression (ga_waypoints_compression.py) on the device:
+    paths f32 / f64 [n, W, 4] cuda -> CODEC_QUANT_F32: f32[n, W, 3] = np.round(w / q) * q (:2090-2093, q = 0.05);
+    CODEC_DELTA_ROUND: f64[n, W, 3] = np.round(np.diff(w, prepend=w[:1]), d) (:875-884, d = 3).  The entropy coder
+    (zlib / LZMA) stays on the host: `zlib.compress(encode_waypoints(p)[0].cpu().numpy().tobytes())`."""
+    if paths.dim() == 2:
+        paths = paths.unsqueeze(0)
+    f32 = paths.dtype == torch.float32
+    _chk_tensor(paths, torch.float32 if f32 else torch.float64, "paths", 3)
+    n, W, four = paths.shape
+    if four != 4:
+        raise ValueError("paths must be [n, W, 4]")
+    if param is None:
+        param = 0.05 if mode == L.CODEC_QUANT_F32 else 3
+    out = torch.empty((n, W, 3), dtype=torch.float32 if mode == L.CODEC_QUANT_F32 else torch.float64, device=paths.device)
+    check(lib.tf_encode_waypoints(_ptr(paths), int(f32), n, W, int(mode), float(param), _ptr(out), _stream()),
+          "tf_encode_waypoints")
+    return out
+
+
 # ------------------------------------------------------------------------------------ host round trips
 class HostStepper:
     """The array API for callers whose populations live in HOST memory (what a drop-in call from

@@ -218,3 +218,49 @@ extern "C" int tf_select_roulette(const double* cum_dev, int P, const double* u_
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------
+// Result egress: the lossy front ends of ga_waypoints_compression.py on the device, one thread per
+// coordinate, float64 arithmetic with explicit roundings (np.round = rint, half to even; decimals d: rint(x 10^d) / 10^d).
+namespace tf {
+template <typename T>
+__global__ void encode_waypoints_kernel(const T* __restrict__ paths, int64_t n, int W, int mode, double param, double scale,
+                                        void* __restrict__ out) {
+    const int64_t total = n * W * 3;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+        const int a = (int)(o % 3);
+        const int64_t wp = o / 3;
+        const int i = (int)(wp % W);
+        const double w = (double)paths[wp * 4 + a];
+        if (mode == TF_CODEC_QUANT_F32) {
+            reinterpret_cast<float*>(out)[o] = __double2float_rn(__dmul_rn(rint(__ddiv_rn(w, param)), param));
+        } else {
+            const double prev = i == 0 ? w : (double)paths[(wp - 1) * 4 + a];
+            reinterpret_cast<double*>(out)[o] = __ddiv_rn(rint(__dmul_rn(__dsub_rn(w, prev), scale)), scale);
+        }
+    }
+}
+}  // namespace tf
+
+extern "C" int tf_encode_waypoints(const void* paths_dev, int f32, int64_t n_paths, int W, int mode, double param,
+                                   void* out_dev, void* stream) {
+    if (!paths_dev || !out_dev) return TF_ERR_INVALID;
+    if (n_paths < 0 || W < 1) return TF_ERR_SHAPE;
+    if (mode != TF_CODEC_QUANT_F32 && mode != TF_CODEC_DELTA_ROUND) return TF_ERR_INVALID;
+    if (mode == TF_CODEC_QUANT_F32 && !(param > 0.0)) return TF_ERR_SHAPE;
+    if (mode == TF_CODEC_DELTA_ROUND && (param < 0.0 || param > 15.0 || param != (double)(int)param)) return TF_ERR_SHAPE;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    if (n_paths == 0) return TF_OK;
+    double scale = 1.0;
+    if (mode == TF_CODEC_DELTA_ROUND) for (int i = 0; i < (int)param; ++i) scale *= 10.0;
+    const int64_t total = n_paths * W * 3, want = (total + 255) / 256, cap = (int64_t)sm_count() * 16;
+    const int grid = (int)(want < cap ? want : cap);
+    if (f32)
+        tf::encode_waypoints_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)paths_dev, n_paths, W, mode, param, scale, out_dev);
+    else
+        tf::encode_waypoints_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)paths_dev, n_paths, W, mode, param, scale, out_dev);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
