@@ -315,6 +315,22 @@ int tf_find_path_pf(const tf_env* env, const double source[3], const double dest
                     const int32_t* height_variation_dev, int n, int dodge, int cap, double* paths64_dev,
                     int32_t* lens_dev, int32_t* overflow_dev, void* stream);
 
+/* ---- initial population of the backend GA --------------------------------------- */
+/* `UAVPathPlanner.find_path()` (GA_enhanced.py GAE:166-179: straight lines GAE:143-151, random one-step dodge
+ * GAE:153-164, voxel-set membership GAE:140-141) for n_paths paths, which is `GeneticAlgorithm.initialize_population`
+ * (GAE:13-18).  The reference draws one random.shuffle per dodge from Python's global generator, path after path, so
+ * the paths are walked IN SEQUENCE by one warp (lanes share the membership scan) and consume shuffles_dev — packed
+ * orders from tf_py_shuffle6_tape — in that order.  obstacles_dev i32[n_obs][4] (x, y, z, 0); bounds = xlo xhi ylo yhi
+ * zlo zhi (inclusive, GAE:132-138).  paths_dev i32[n_paths][cap][4]; lens_dev i32[n_paths];
+ * result_dev i32[2] = {shuffles consumed, status: 0 ok / 1 cap too small / 2 tape exhausted}. */
+int tf_find_path_gae(const int32_t* obstacles_dev, int n_obs, const int32_t bounds[6], const int32_t source[3],
+                     const int32_t destination[3], const int32_t* shuffles_dev, int n_shuffles, int n_paths, int cap,
+                     int32_t* paths_dev, int32_t* lens_dev, int32_t* result_dev, void* stream);
+/* n shuffles of the six dodge moves, taken from a COPY of CPython's global generator (random.getstate()[1]: 624 key
+ * words, then the position) exactly as random.shuffle takes them (host function).  out[i]: the order, 3 bits per
+ * position.  mt_key / *mt_pos are updated to the state after the draws. */
+int tf_py_shuffle6_tape(uint32_t* mt_key, int32_t* mt_pos, int n, int32_t* out);
+
 /* ---- compact host format -------------------------------------------------- */
 /* int16[n][4] (x, y, z, pad) <-> f32[n][4]: lattice chromosomes at 8 B per waypoint for the PCIe leg.
  * Packing rounds to nearest and saturates; it is exact for integer coordinates in [-32768, 32767]. */

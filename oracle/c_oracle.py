@@ -247,6 +247,23 @@ def encode_waypoints(paths, mode, param):
     return out
 
 
+def find_path_gae(obstacles, bounds, src, dst, shuffles, n_paths, cap=512):
+    """UAVPathPlanner.find_path (GAE:166-179) for n_paths in sequence; shuffles: packed random.shuffle orders.
+    -> (paths i32[n, cap, 4], lens i32[n], consumed, status)"""
+    obs = np.zeros((len(obstacles), 4), np.int32)
+    if len(obstacles):
+        obs[:, :3] = np.asarray(obstacles, np.int32).reshape(len(obstacles), -1)[:, :3]
+    b = np.ascontiguousarray(np.asarray(bounds, np.int32).reshape(6))
+    s3, d3 = np.asarray(src, np.int32), np.asarray(dst, np.int32)
+    sh = np.ascontiguousarray(shuffles, np.int32)
+    paths = np.zeros((n_paths, cap, 4), np.int32)
+    lens = np.zeros(n_paths, np.int32)
+    used, status = C.c_int32(0), C.c_int32(0)
+    lib().orc_find_path_gae(_p(obs), len(obs), _p(b), _p(s3), _p(d3), _p(sh), len(sh), n_paths, cap, _p(paths), _p(lens),
+                            C.byref(used), C.byref(status))
+    return paths, lens, used.value, status.value
+
+
 def voxel_words(nx, ny, nz):
     return (nx // 8) * (ny // 8) * (nz // 8) * 16
 

@@ -381,7 +381,7 @@ def gen_find_path_pf(pf):
 def main():
     hr = ref_loader.load_hr()
     pf = ref_loader.load_pf()
-    which = set(sys.argv[1:]) or {"fitness", "evolve", "gae", "find_path", "ops_pf", "lidar", "codecs"}
+    which = set(sys.argv[1:]) or {"fitness", "evolve", "gae", "find_path", "ops_pf", "lidar", "codecs", "find_path_gae"}
     if "fitness" in which:
         gen_fitness_hr(hr)
         gen_fitness_pf(pf)
@@ -409,6 +409,8 @@ def main():
         gen_downsample_lidar()
     if "codecs" in which:
         gen_waypoint_codecs()
+    if "find_path_gae" in which:
+        gen_find_path_gae()
 
 
 
@@ -543,6 +545,53 @@ def gen_waypoint_codecs():
     meta = dict(META, ref="ga_waypoints_compression.py:875-885,2090-2094", cases=list(routes), zlib=zlib.ZLIB_VERSION)
     np.savez_compressed(os.path.join(HERE, "waypoint_codecs.npz"), meta=np.array(json.dumps(meta)), **out)
     print("waypoint_codecs.npz:", {k: v.shape for k, v in routes.items()})
+
+
+
+# --------------------------------------------------------------------------- GAE initial paths (find_path)
+def gen_find_path_gae():
+    """UAVPathPlanner.find_path (GA_enhanced.py GAE:166-179) on the file's own voxel Environment (GAE:87-122), P paths
+    per scenario exactly as GeneticAlgorithm.initialize_population builds them (GAE:13-18).  random.shuffle is wrapped
+    to record the order every dodge ends up with (GAE:157) — the "shuffle tape"."""
+    gae = ref_loader.load_gae_classes()
+    moves = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+    scen = [  # seed, bounds, random obstacles, source, destination, P
+        (11, ((0, 30), (0, 30), (0, 15)), 30, (0, 0, 0), (30, 30, 15), 20),       # the golden GAE run's world
+        (12, ((0, 100), (0, 50), (0, 100)), 20, (1, 2, 3), (97, 45, 88), 12),     # SIMR:21 bounds
+        (13, ((0, 12), (0, 12), (0, 6)), 200, (0, 0, 0), (12, 12, 6), 16),        # dense: many dodges
+        (14, ((0, 30), (0, 30), (0, 15)), 30, (30, 2, 14), (0, 29, 0), 8),        # negative directions
+        (15, ((0, 30), (0, 30), (0, 15)), 30, (5, 5, 5), (5, 5, 5), 3),           # source == destination
+    ]
+    out = {}
+    for seed, bounds, nrand, src, dst, P in scen:
+        random.seed(seed)
+        np.random.seed(seed)
+        env = gae.Environment(*bounds, num_random_obstacles=nrand)
+        orders = []
+        orig = random.shuffle
+
+        def rec(x, _orig=orig):
+            _orig(x)
+            orders.append(sum(moves.index(m) << (3 * i) for i, m in enumerate(x)))
+
+        random.shuffle = rec
+        try:
+            paths = [gae.UAVPathPlanner(src, dst, env).find_path() for _ in range(P)]
+        finally:
+            random.shuffle = orig
+        after = random.random()
+        Wmax = max(len(p) for p in paths)
+        wp = np.zeros((P, Wmax, 3), np.int32)
+        lens = np.zeros(P, np.int32)
+        for i, pth in enumerate(paths):
+            lens[i] = len(pth)
+            wp[i, :len(pth)] = np.array(pth, np.int32)
+        out.update({f"obs_{seed}": np.array(sorted(env.obstacles), np.int32), f"bounds_{seed}": np.array(bounds, np.int32),
+                    f"src_{seed}": np.array(src, np.int32), f"dst_{seed}": np.array(dst, np.int32), f"wp_{seed}": wp,
+                    f"lens_{seed}": lens, f"shuffles_{seed}": np.array(orders, np.int32), f"after_{seed}": np.array(after)})
+        print(f"find_path_gae scenario {seed}: {P} paths, lens {int(lens.min())}..{int(lens.max())}, {len(orders)} dodges")
+    meta = dict(META, ref="GAE:125-179", scenarios=[s[0] for s in scen])
+    np.savez_compressed(os.path.join(HERE, "find_path_gae.npz"), meta=np.array(json.dumps(meta)), **out)
 
 
 

@@ -43,3 +43,41 @@ def test_fitness_gae_kernel_vs_oracle():
     assert np.array_equal(got, O.fitness_gae(pop, lens))
     got = B.fitness_gae(torch.from_numpy(pop).cuda(), None).cpu().numpy()
     assert np.array_equal(got, O.fitness_gae(pop, None))
+
+
+def test_find_path_gae_kernel_vs_reference_walks():
+    """tf_find_path_gae against the walks of the unmodified UAVPathPlanner (tests/golden/find_path_gae.npz), fed the
+    recorded shuffle orders through the C-ABI, and through batched.find_path_gae (natively drawn tape under the same
+    random.seed): same paths, same generator state afterwards."""
+    import ctypes as C
+    import json
+    import os
+    import random
+    import torch
+    from tracefly_b200 import _lib as L, batched as B
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "find_path_gae.npz"))
+    for seed in json.loads(str(g["meta"]))["scenarios"]:
+        wp, lens, sh = g[f"wp_{seed}"], g[f"lens_{seed}"], g[f"shuffles_{seed}"]
+        obs = np.zeros((len(g[f"obs_{seed}"]), 4), np.int32)
+        obs[:, :3] = g[f"obs_{seed}"]
+        P, cap = len(lens), int(lens.max()) + 3
+        paths = torch.zeros((P, cap, 4), dtype=torch.int32, device="cuda")
+        dl = torch.zeros(P, dtype=torch.int32, device="cuda")
+        res = torch.zeros(2, dtype=torch.int32, device="cuda")
+        i3 = lambda v: (C.c_int32 * 3)(*[int(x) for x in v])
+        b6 = (C.c_int32 * 6)(*[int(v) for v in g[f"bounds_{seed}"].reshape(6)])
+        shd = torch.from_numpy(np.ascontiguousarray(sh if len(sh) else np.zeros(1, np.int32))).cuda()
+        obs_d = torch.from_numpy(obs).cuda()
+        L.check(L.lib.tf_find_path_gae(obs_d.data_ptr(), len(obs), b6, i3(g[f"src_{seed}"]), i3(g[f"dst_{seed}"]),
+                                       shd.data_ptr(), len(sh), P, cap, paths.data_ptr(), dl.data_ptr(), res.data_ptr(), None), "tf_find_path_gae")
+        assert res.cpu().tolist() == [len(sh), 0]
+        assert np.array_equal(dl.cpu().numpy(), lens)
+        got = paths.cpu().numpy()
+        for i in range(P):
+            assert np.array_equal(got[i, :lens[i], :3], wp[i, :lens[i]]), (seed, i)
+        random.seed(int(seed))
+        trails = B.find_path_gae([tuple(o) for o in g[f"obs_{seed}"].tolist()], g[f"bounds_{seed}"].tolist(),
+                                 g[f"src_{seed}"].tolist(), g[f"dst_{seed}"].tolist(), P, cap=8)   # forces the capacity retry
+        assert [len(t) for t in trails] == lens.tolist()
+        assert all(np.array_equal(np.array(t), wp[i, :lens[i]]) for i, t in enumerate(trails))
+        assert random.random() == float(g[f"after_{seed}"])

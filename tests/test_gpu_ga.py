@@ -394,6 +394,62 @@ def test_waypoint_codecs_on_device(tf):
         B.encode_waypoints(pop, L.CODEC_QUANT_F32, 0.0)
 
 
+def test_malformed_tapes_are_clamped_not_trusted(tf):
+    """A host tape with out-of-range ranks / indices / crossover points (evolve_batch(tapes=...) accepts user tapes)
+    is clamped on the device — no out-of-bounds parent gather — and the oracle clamps the same way."""
+    torch, L, B = tf
+    rng = np.random.default_rng(2)
+    P, W = 600, 32
+    pop = B.init_walks(4, P, W, start=(9, 9, 9), lo=(0, 0, 0), hi=(30, 30, 30))
+    fit = torch.from_numpy(rng.random(P).astype(np.float32)).cuda()
+    npairs = (P - 2 + 1) // 2
+    tape = np.zeros((npairs, 8), np.int32)
+    tape[:, 0] = rng.integers(-5, 2000, size=npairs)
+    tape[:, 1] = rng.integers(-2_000_000, 2_000_000, size=npairs)
+    tape[:, 2] = rng.integers(-10, 700, size=npairs)
+    tape[:, 3] = rng.integers(-1, 40, size=npairs)
+    tape[:, 5] = rng.integers(-1, 40, size=npairs)
+    tape[:, 4] = tape[:, 6] = 0b100100
+    env, prm = B.Environment.empty(), L.default_params()
+    for sel_mode, k in ((L.SEL_TRUNCATION, 10), (L.SEL_TOURNAMENT, 2), (L.SEL_TOP2, 2)):
+        top = B.rank_topk(fit, k)
+        ga = L.default_ga_params(n_elite=2, selection=sel_mode, n_top=10)
+        oga = O.default_ga(n_elite=2, selection=int(sel_mode), n_top=10)
+        onxt, _, osel, ocp = O.ga_step(pop.cpu().numpy(), fit.cpu().numpy(), top.cpu().numpy(), oga, tape=tape)
+        nxt, _, sel, cp = B.ga_step(pop, fit, top, ga, tape=tape)
+        assert np.array_equal(osel, sel.cpu().numpy()) and np.array_equal(ocp, cp.cpu().numpy())
+        assert np.array_equal(onxt, nxt.cpu().numpy())
+        fnxt, _, _, fsel, fcp = B.generation(env, pop, fit, top, ga, prm, tape=tape, want_parity=True)
+        assert torch.equal(fnxt, nxt) and torch.equal(fsel, sel) and torch.equal(fcp, cp)
+        assert int(sel.min()) >= 0 and int(sel.max()) < P and int(cp.min()) >= 0 and int(cp.max()) <= W
+
+
+def test_generation_falls_back_to_the_unfused_pair_for_large_tables(tf):
+    """More than 2048 analytic obstacles and no candidate index: tf_generation answers TF_ERR_UNSUPPORTED and
+    batched.generation / evolve_batch take tf_ga_step + tf_fitness — same results as the oracle."""
+    torch, L, B = tf
+    rng = np.random.default_rng(6)
+    table = random_table(rng, 2500, 64, sem_pf=True)
+    env, prm = B.Environment(L.SEM_PF, table, 0.0), L.default_params(dist_zero_guard=0)
+    oenv = oracle_env_from_table(O.SEM_PF, table, 0.0)
+    P, W = 300, 32
+    pop = B.init_walks(4, P, W, start=(30, 30, 30), lo=(0, 0, 0), hi=(63, 63, 63))
+    fit, _ = B.fitness_batch(pop, None, env, prm)
+    top = B.rank_topk(fit, 2)
+    ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=3, mutation_rate=0.5)
+    assert L.lib.tf_generation(env.handle, pop.data_ptr(), fit.data_ptr(), top.data_ptr(), None, 1, 2, ga, prm, P, W,
+                               torch.empty_like(pop).data_ptr(), torch.empty_like(fit).data_ptr(), None, None, None,
+                               None) == L.TF_ERR_UNSUPPORTED
+    nxt, nfit, ncoll, sel, cp = B.generation(env, pop, fit, top, ga, prm, seed=1, generation=2, want_collisions=True, want_parity=True)
+    oga = O.default_ga(selection=1, tournament_k=3, mutation_rate=0.5)
+    onxt, _, osel, ocp = O.ga_step(pop.cpu().numpy(), fit.cpu().numpy(), top.cpu().numpy(), oga, seed=1, gen=2)
+    onfit, oncoll = O.fitness_f32(oenv, onxt, None, O.default_params(guard=0))
+    assert np.array_equal(onxt, nxt.cpu().numpy()) and np.array_equal(osel, sel.cpu().numpy())
+    assert np.array_equal(onfit, nfit.cpu().numpy()) and np.array_equal(oncoll, as_u32(ncoll))
+    res = B.evolve_batch(pop, env, 3, ga, prm, seed=1)
+    assert res["generation"] == 3
+
+
 def test_evolve_batch_resume_is_bit_identical(tf, tmp_path):
     """Checkpoint / resume: Philox is counter-based, so 12 generations == 5 + resume + 7."""
     torch, L, B = tf

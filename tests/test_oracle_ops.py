@@ -130,3 +130,48 @@ def test_waypoint_codecs_vs_reference(case):
         assert np.array_equal(np.frombuffer(zlib.compress(q.tobytes()), np.uint8), g[f"zlib_{case}"])
     d = O.encode_waypoints(p4, 1, 3)[0]
     assert np.array_equal(d.view(np.uint64), g[f"dq_{case}"].view(np.uint64))
+
+
+def _gae_scenarios():
+    g = np.load(os.path.join(GOLD, "find_path_gae.npz"))
+    return g, json.loads(str(g["meta"]))["scenarios"]
+
+
+@pytest.mark.parametrize("seed", _gae_scenarios()[1])
+def test_find_path_gae_vs_reference(seed):
+    """orc_find_path_gae == UAVPathPlanner.find_path of the unmodified GA_enhanced.py (GAE:166-179) on its own voxel
+    world, with the recorded random.shuffle orders: every path, waypoint for waypoint, and the shuffle count."""
+    g, _ = _gae_scenarios()
+    wp, lens, sh = g[f"wp_{seed}"], g[f"lens_{seed}"], g[f"shuffles_{seed}"]
+    bounds = g[f"bounds_{seed}"].reshape(6)
+    P, cap = len(lens), int(lens.max()) + 5
+    paths, olens, used, status = O.find_path_gae(g[f"obs_{seed}"], bounds, g[f"src_{seed}"], g[f"dst_{seed}"], sh, P, cap)
+    assert status == 0 and used == len(sh)
+    assert np.array_equal(olens, lens)
+    for i in range(P):
+        assert np.array_equal(paths[i, :lens[i], :3], wp[i, :lens[i]]), i
+    if len(sh):      # too short a tape / too small a capacity are reported, not silently truncated
+        assert O.find_path_gae(g[f"obs_{seed}"], bounds, g[f"src_{seed}"], g[f"dst_{seed}"], sh[:-1], P, cap)[3] == 2
+    if lens.max() > 1:
+        assert O.find_path_gae(g[f"obs_{seed}"], bounds, g[f"src_{seed}"], g[f"dst_{seed}"], sh, P, int(lens.max()) - 1)[3] == 1
+
+
+@pytest.mark.parametrize("seed", _gae_scenarios()[1])
+def test_native_shuffle_tape_is_random_shuffle(seed):
+    """tf_py_shuffle6_tape (host function of the C-ABI) == the orders random.shuffle produced inside the reference's
+    dodge_obstacle (GAE:157), and it leaves CPython's generator where the reference left it."""
+    import ctypes as C
+    import __graft_entry__ as ge
+    ge.build()
+    from tracefly_b200 import _lib as L
+    g, _ = _gae_scenarios()
+    sh = g[f"shuffles_{seed}"]
+    random.seed(int(seed))
+    st = random.getstate()
+    key = np.array(st[1][:624], np.uint32)
+    pos = C.c_int32(int(st[1][624]))
+    out = np.zeros(max(len(sh), 1), np.int32)
+    assert L.lib.tf_py_shuffle6_tape(key.ctypes.data_as(C.c_void_p), C.byref(pos), len(sh), out.ctypes.data_as(C.c_void_p)) == 0
+    assert np.array_equal(out[:len(sh)], sh)
+    random.setstate((st[0], tuple(int(v) for v in key) + (pos.value,), st[2]))
+    assert random.random() == float(g[f"after_{seed}"])

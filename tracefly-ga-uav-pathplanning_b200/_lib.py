@@ -57,6 +57,8 @@ _SIGS = {
     "tf_voxel_grid_bytes": (_i64, [_i, _i, _i]),
     "tf_voxelize": (_i, [_i, _vp, _i, _f, _vp, _i, _i, _i, _vp]),
     "tf_voxelize_points": (_i, [_vp, _i64, C.POINTER(_d), _d, _vp, _i, _i, _i, _vp]),
+    "tf_find_path_gae": (_i, [_vp, _i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "tf_py_shuffle6_tape": (_i, [_vp, _vp, _i, _vp]),
     "tf_encode_waypoints": (_i, [_vp, _i, _i64, _i, _i, _d, _vp, _vp]),
     "tf_roulette_cumweights": (_i, [_vp, _i, _vp, _vp]),
     "tf_select_roulette": (_i, [_vp, _i, _vp, _i, _vp, _vp]),

@@ -334,6 +334,57 @@ def find_path_pf(env, source, destination, height_variations, dodge="up", cap=64
         cap *= 2
 
 
+def find_path_gae(obstacles, bounds, source, destination, n_paths, cap=256, max_cap=1 << 16):
+    """`UAVPathPlanner.find_path()` of the backend GA (GAE:166-179) n_paths times — what
+    `GeneticAlgorithm.initialize_population` does (GAE:13-18) — in ONE launch.  The dodges take their
+    `random.shuffle` orders from a tape drawn natively from a copy of CPython's global generator
+    (tf_py_shuffle6_tape); afterwards the generator is advanced by exactly the shuffles the walks consumed, so the
+    caller's `random` stream continues as it would after the reference's own loop.
+    obstacles: iterable of integer voxels; bounds: ((xlo, xhi), (ylo, yhi), (zlo, zhi)) inclusive.
+    -> list of n_paths lists of (x, y, z) int tuples."""
+    import random
+    _require_cuda()
+    obs = np.zeros((len(obstacles), 4), np.int32)
+    if len(obstacles):
+        obs[:, :3] = np.asarray(list(obstacles), np.int64).reshape(len(obstacles), -1)[:, :3]
+    obs_d = torch.from_numpy(obs).cuda()
+    i3 = lambda v: (C.c_int32 * 3)(*[int(x) for x in v])
+    b6 = (C.c_int32 * 6)(*[int(v) for pair in bounds for v in pair])
+    state = random.getstate()
+    key0 = np.array(state[1][:624], np.uint32)
+    pos0 = int(state[1][624])
+
+    def tape(n):
+        key, pos = key0.copy(), C.c_int32(pos0)
+        out = np.zeros(max(n, 1), np.int32)
+        check(lib.tf_py_shuffle6_tape(key.ctypes.data_as(C.c_void_p), C.byref(pos), n, out.ctypes.data_as(C.c_void_p)),
+              "tf_py_shuffle6_tape")
+        return out, key, pos.value
+
+    n_sh = 64 * max(n_paths, 1)
+    while True:
+        orders, _, _ = tape(n_sh)
+        sh_d = torch.from_numpy(orders).cuda()
+        paths = torch.empty((max(n_paths, 1), cap, 4), dtype=torch.int32, device="cuda")
+        lens = torch.zeros(max(n_paths, 1), dtype=torch.int32, device="cuda")
+        res = torch.zeros(2, dtype=torch.int32, device="cuda")
+        check(lib.tf_find_path_gae(_ptr(obs_d), len(obs), b6, i3(source), i3(destination), _ptr(sh_d), n_sh, n_paths, cap,
+                                   _ptr(paths), _ptr(lens), _ptr(res), _stream()), "tf_find_path_gae")
+        used, status = (int(v) for v in res.cpu().tolist())
+        if status == 0:
+            break
+        if status == 1:
+            if cap >= max_cap:
+                raise RuntimeError(f"find_path_gae: a path needs more than {max_cap} waypoints")
+            cap *= 2
+        else:
+            n_sh *= 4
+    _, key, pos = tape(used)                                  # advance the caller's generator by what was consumed
+    random.setstate((state[0], tuple(int(v) for v in key) + (pos,), state[2]))
+    rows, counts = paths.cpu().numpy(), lens.cpu().numpy()
+    return [[tuple(int(v) for v in w[:3]) for w in rows[i, :counts[i]]] for i in range(n_paths)]
+
+
 # ------------------------------------------------------------------------------------ ranking
 class TopK:
     """Reusable top-k plan (owns the workspace): order = (fitness desc, index asc) — the stable
@@ -428,9 +479,18 @@ def generation(env, pop, fit, top_idx, ga=None, params=None, tape=None, seed=0, 
     coll = torch.empty((P, (W + 31) // 32), dtype=torch.int32, device=pop.device) if want_collisions else None
     sel = torch.empty((npairs, 2), dtype=torch.int32, device=pop.device) if want_parity else None
     cp = torch.empty(npairs, dtype=torch.int32, device=pop.device) if want_parity else None
-    check(lib.tf_generation(env.handle, _ptr(pop), _ptr(fit), _ptr(top_idx), _ptr(tape), seed, generation,
-                            C.byref(ga), C.byref(params), P, W, _ptr(nxt), _ptr(nfit), _ptr(coll), _ptr(sel), _ptr(cp),
-                            _stream()), "tf_generation")
+    rc = lib.tf_generation(env.handle, _ptr(pop), _ptr(fit), _ptr(top_idx), _ptr(tape), seed, generation,
+                           C.byref(ga), C.byref(params), P, W, _ptr(nxt), _ptr(nfit), _ptr(coll), _ptr(sel), _ptr(cp),
+                           _stream())
+    if rc == L.TF_ERR_UNSUPPORTED:
+        # more than 2048 analytic obstacles without a candidate index: the fused kernel stages one table chunk only.
+        # The unfused pair gives the same results (tf_ga_step + tf_fitness walk the table in chunks).
+        check(lib.tf_ga_step(_ptr(pop), None, _ptr(fit), _ptr(top_idx), _ptr(tape), seed, generation, C.byref(ga), P, W,
+                             _ptr(nxt), None, _ptr(sel), _ptr(cp), _stream()), "tf_ga_step")
+        check(lib.tf_fitness(env.handle, _ptr(nxt), None, P, W, C.byref(params), _ptr(nfit), _ptr(coll), _stream()),
+              "tf_fitness")
+        return nxt, nfit, coll, sel, cp
+    check(rc, "tf_generation")
     return nxt, nfit, coll, sel, cp
 
 

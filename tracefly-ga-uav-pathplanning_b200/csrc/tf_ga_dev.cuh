@@ -57,9 +57,17 @@ __device__ __forceinline__ ChildPlan<NW> plan_child(int slot, int ne, const F* _
     U4 r = U4{0, 0, 0, 0};
     if (tape != nullptr) {
         const tf_draw t = tape[j];
-        ia = ga.selection != TF_SEL_TOURNAMENT ? top_idx[t.pa] : t.pa;   // truncation / top-2: ranks; tournament: indices
-        ib = ga.selection != TF_SEL_TOURNAMENT ? top_idx[t.pb] : t.pb;
-        cp = t.cp;
+        // a host-supplied tape is clamped, never trusted: ranks to the ranked pool, indices to the population, the
+        // crossover point to [0, W] (a valid tape passes through unchanged; the oracle clamps the same way)
+        if (ga.selection != TF_SEL_TOURNAMENT) {   // truncation / top-2: ranks into top_idx
+            const int pool = max(1, min(P, ga.selection == TF_SEL_TOP2 ? 2 : max(ga.n_top, 1)));
+            ia = top_idx[min(max(t.pa, 0), pool - 1)];
+            ib = top_idx[min(max(t.pb, 0), pool - 1)];
+        } else {                                   // tournament: population indices
+            ia = min(max(t.pa, 0), P - 1);
+            ib = min(max(t.pb, 0), P - 1);
+        }
+        cp = min(max(t.cp, 0), W);
         mp = c == 0 ? t.mp1 : t.mp2;
         const int d = c == 0 ? t.d1 : t.d2;
         pl.dx = (float)((d & 3) - 1);

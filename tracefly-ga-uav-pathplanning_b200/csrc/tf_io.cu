@@ -264,3 +264,79 @@ extern "C" int tf_encode_waypoints(const void* paths_dev, int f32, int64_t n_pat
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------
+// Backend GA initial population: UAVPathPlanner.find_path (GAE:166-179) for n paths in sequence, one
+// warp; the 32 lanes share the voxel-set membership scan (GAE:140-141: `point in obstacles`).  float64 straight lines
+// (GAE:143-151, np.linspace + round-half-even), shuffles from the host tape (GAE:157).
+namespace tf {
+__device__ __forceinline__ bool gae_hit(const int4* __restrict__ obs, int n_obs, int x, int y, int z) {
+    bool hit = false;
+    for (int k = threadIdx.x; k < n_obs && !hit; k += 32) {
+        const int4 o = __ldg(obs + k);
+        hit = o.x == x && o.y == y && o.z == z;
+    }
+    return __any_sync(0xffffffffu, hit);
+}
+__global__ void __launch_bounds__(32)
+find_path_gae_kernel(const int4* __restrict__ obs, int n_obs, int xlo, int xhi, int ylo, int yhi, int zlo, int zhi, int sx,
+                     int sy, int sz, int dx, int dy, int dz, const int32_t* __restrict__ shuffles, int n_shuffles, int n_paths,
+                     int cap, int4* __restrict__ paths, int32_t* __restrict__ lens, int32_t* __restrict__ result) {
+    const int mvx[6] = {1, -1, 0, 0, 0, 0}, mvy[6] = {0, 0, 1, -1, 0, 0}, mvz[6] = {0, 0, 0, 0, 1, -1};
+    int used = 0, status = 0;
+    for (int p = 0; p < n_paths && status == 0; ++p) {
+        int4* out = paths + (size_t)p * cap;
+        int cx = sx, cy = sy, cz = sz, len = 1;
+        if (threadIdx.x == 0) out[0] = make_int4(cx, cy, cz, 0);
+        while (!(cx == dx && cy == dy && cz == dz) && status == 0) {
+            const int ax = cx, ay = cy, az = cz;                       // the line starts where the planner stands
+            const int steps = max(max(abs(dx - ax), abs(dy - ay)), abs(dz - az));
+            const double inv = __ddiv_rn(1.0, (double)steps);
+            for (int i = 0; i <= steps; ++i) {
+                const double t = i == steps ? 1.0 : __dmul_rn((double)i, inv);
+                const int qx = (int)rint(__dadd_rn((double)ax, __dmul_rn(t, (double)(dx - ax))));
+                const int qy = (int)rint(__dadd_rn((double)ay, __dmul_rn(t, (double)(dy - ay))));
+                const int qz = (int)rint(__dadd_rn((double)az, __dmul_rn(t, (double)(dz - az))));
+                if (gae_hit(obs, n_obs, qx, qy, qz)) {                   // GAE:170-172
+                    if (used >= n_shuffles) { status = 2; break; }
+                    const int order = __ldg(shuffles + used++);
+                    for (int m = 0; m < 6; ++m) {                        // GAE:157-163
+                        const int k = (order >> (3 * m)) & 7;
+                        const int nx = cx + mvx[k], ny = cy + mvy[k], nz = cz + mvz[k];
+                        if (nx >= xlo && nx <= xhi && ny >= ylo && ny <= yhi && nz >= zlo && nz <= zhi &&
+                            !gae_hit(obs, n_obs, nx, ny, nz)) {
+                            cx = nx; cy = ny; cz = nz;
+                            break;
+                        }
+                    }
+                    break;
+                }
+                if (len == cap) { status = 1; break; }
+                if (threadIdx.x == 0) out[len] = make_int4(qx, qy, qz, 0);
+                ++len;
+                cx = qx; cy = qy; cz = qz;
+                if (cx == dx && cy == dy && cz == dz) break;
+            }
+        }
+        if (threadIdx.x == 0) lens[p] = len;
+    }
+    if (threadIdx.x == 0) { result[0] = used; result[1] = status; }
+}
+}  // namespace tf
+
+extern "C" int tf_find_path_gae(const int32_t* obstacles_dev, int n_obs, const int32_t bounds[6], const int32_t source[3],
+                                const int32_t destination[3], const int32_t* shuffles_dev, int n_shuffles, int n_paths,
+                                int cap, int32_t* paths_dev, int32_t* lens_dev, int32_t* result_dev, void* stream) {
+    if (!bounds || !source || !destination || !paths_dev || !lens_dev || !result_dev) return TF_ERR_INVALID;
+    if ((n_obs > 0 && !obstacles_dev) || (n_shuffles > 0 && !shuffles_dev)) return TF_ERR_INVALID;
+    if (n_obs < 0 || n_shuffles < 0 || n_paths < 0 || cap < 1) return TF_ERR_SHAPE;
+    int rc = ensure_device();
+    if (rc != TF_OK) return rc;
+    tf::find_path_gae_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const int4*>(obstacles_dev), n_obs, bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5],
+        source[0], source[1], source[2], destination[0], destination[1], destination[2], shuffles_dev, n_shuffles, n_paths,
+        cap, reinterpret_cast<int4*>(paths_dev), lens_dev, result_dev);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}

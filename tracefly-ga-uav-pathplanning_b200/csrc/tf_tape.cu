@@ -102,3 +102,34 @@ extern "C" int tf_np_hr_tape(uint32_t* mt_key, int32_t* mt_pos, int generations,
     *mt_pos = s.pos;
     return TF_OK;
 }
+
+// random.shuffle of the six axis moves in UAVPathPlanner.dodge_obstacle (GAE:150-157), `n` times, from a COPY of
+// CPython's global Mersenne Twister (random.getstate()[1]: 624 key words + position):
+//   shuffle(x): for i in reversed(range(1, len(x))): j = _randbelow(i + 1); x[i], x[j] = x[j], x[i]
+//   _randbelow(n): k = n.bit_length(); r = getrandbits(k); while r >= n: r = getrandbits(k)
+//   getrandbits(k <= 32) = genrand_uint32() >> (32 - k)
+// out[s] packs the shuffled order of moves 0..5 (GAE:151-155 list order), 3 bits per position, first move lowest.
+extern "C" int tf_py_shuffle6_tape(uint32_t* mt_key, int32_t* mt_pos, int n, int32_t* out) {
+    if (!mt_key || !mt_pos || (n > 0 && !out)) return TF_ERR_INVALID;
+    if (n < 0 || *mt_pos < 0 || *mt_pos > 624) return TF_ERR_SHAPE;
+    MT s;
+    memcpy(s.key, mt_key, sizeof(s.key));
+    s.pos = *mt_pos;
+    for (int r = 0; r < n; ++r) {
+        int x[6] = {0, 1, 2, 3, 4, 5};
+        for (int i = 5; i >= 1; --i) {
+            const uint32_t lim = (uint32_t)(i + 1);
+            int k = 0;
+            while ((lim >> k) != 0u) ++k;                  // bit_length
+            uint32_t j;
+            do { j = mt_next(s) >> (32 - k); } while (j >= lim);
+            const int tmp = x[i]; x[i] = x[(int)j]; x[(int)j] = tmp;
+        }
+        int32_t packed = 0;
+        for (int i = 0; i < 6; ++i) packed |= x[i] << (3 * i);
+        out[r] = packed;
+    }
+    memcpy(mt_key, s.key, sizeof(s.key));
+    *mt_pos = s.pos;
+    return TF_OK;
+}

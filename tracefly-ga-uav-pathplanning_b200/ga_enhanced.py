@@ -21,6 +21,7 @@ same seeds returns upstream's path (tests/test_gpu_dropin_gae.py, golden recorde
 Upstream behaviour that is reproduced on purpose
   * roulette weights are score / total with both negative, so WORSE paths are favoured (GAE:30-33);
   * `find_path` appends the point it is standing on again at the start of every straight run (GAE:166-179);
+    the whole initial population is one `tf_find_path_gae` launch (the reference's greedy walker on the device);
   * fitness is the integer  -len - #{i : path[i-1] != path[i+1]}  (GAE:20-26).
 Deliberate differences
   * `mutate` dodges inside the environment given to `run()`; upstream reads a module-level global that
@@ -78,6 +79,19 @@ class GeneticAlgorithm:
 
     # -- upstream's method names -------------------------------------------------------------
     def initialize_population(self, source, destination, environment):
+        """GAE:13-18: population_size walks of UAVPathPlanner.find_path.  With integer endpoints and bounds they run
+        in one tf_find_path_gae launch (same paths, same consumption of `random`: the dodges read a natively drawn
+        shuffle tape); anything else takes the host planner below."""
+        def whole(values):
+            return all(isinstance(v, (int, np.integer)) and not isinstance(v, bool) for v in values)
+        limits = (environment.x_bounds, environment.y_bounds, environment.z_bounds)
+        if self.population_size > 0 and whole(source) and whole(destination) and all(whole(b) for b in limits) \
+                and all(whole(o) for o in environment.obstacles):
+            first = tuple(source)
+            for trail in B.find_path_gae(environment.obstacles, limits, source, destination, self.population_size):
+                trail[0] = first                                  # upstream keeps the caller's tuple first
+                self.population.append(trail)
+            return
         self.population.extend(UAVPathPlanner(source, destination, environment).find_path()
                                for _ in range(self.population_size))
 
