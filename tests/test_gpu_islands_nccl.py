@@ -1,0 +1,26 @@
+"""Multi-GPU parity in the -m gpu suite: the product island path (CudaOps + NCCL all-gather, one process per GPU under
+torchrun) against the single-process CPU restatement of the whole world (oracle/islands_sim.py), bit for bit, in
+both schedules.  Needs two visible B200s; with one GPU the test is skipped (tests/test_islands_gloo.py covers the
+host logic on CPU, test_gpu_ga.py the exchange kernels on one GPU)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_islands_over_nccl_equal_the_cpu_restatement():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    port = 29600 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "islands_nccl_check.py")]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    ok = [l for l in r.stdout.splitlines() if "identical to the restatement: True" in l]
+    assert len(ok) == 4, r.stdout[-3000:]          # 2 ranks x 2 schedules

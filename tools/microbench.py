@@ -65,10 +65,32 @@ def main():
     out["sum_pop(torch.sum, read only)"] = timeit(torch, lambda: torch.sum(pop))
     src = torch.empty_like(pop)
     out["copy_pop_d2d(torch)"] = timeit(torch, lambda: src.copy_(pop))
+    # ---- the variants that stay on the LSU path (tf_stream_host.cuh: stream_eligible): uniform crossover, S > 1
+    #      samples per segment, ragged lengths — north_star names the first two; their roofline fractions
+    peak = bench.measured_peak_gbs()[0]
+    gau = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=4, crossover=L.CX_UNIFORM, mutation=L.MUT_GAUSSIAN,
+                              mutation_rate=0.1, sigma=1.5, n_elite=2)
+    out["generation_fused_uniform_crossover_gaussian_mutation(LSU path)"] = timeit(
+        torch, lambda: B.generation(env, pop, fit, top, gau, params, seed=1, generation=1, out_pop=nxt, out_fit=nfit))
+    gam = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=4, mutation=L.MUT_GAUSSIAN, mutation_rate=0.1, sigma=1.5, n_elite=2)
+    out["generation_fused_single_point_gaussian_mutation(TMA path)"] = timeit(
+        torch, lambda: B.generation(env, pop, fit, top, gam, params, seed=1, generation=1, out_pop=nxt, out_fit=nfit))
+    p3 = L.Params.from_buffer_copy(params)
+    p3.samples_per_segment = 3
+    out["fitness_S3_samples_per_segment(LSU path)"] = timeit(torch, lambda: B.fitness_batch(pop, None, env, p3, out=fit, want_collisions=False), n=10)
+    lens = torch.full((P,), W, dtype=torch.int32, device="cuda")
+    lens[::3] = W - 7
+    out["fitness_ragged_lengths(LSU path)"] = timeit(torch, lambda: B.fitness_batch(pop, lens, env, params, out=fit, want_collisions=False))
+    B.fitness_batch(pop, None, env, params, out=fit, want_collisions=False)
     bytes_gen = (32 * W + 12) * P
     rep = {k: {"median_ms": v[0], "min_ms": v[1]} for k, v in out.items()}
     rep["generation_fused"]["algorithmic_GBs"] = bytes_gen / (out["generation_fused"][0] * 1e-3) / 1e9
     rep["fitness"]["algorithmic_GBs"] = (16 * W + 4) * P / (out["fitness"][0] * 1e-3) / 1e9
+    for k in rep:
+        if k.startswith("generation_fused"):
+            rep[k]["frac_of_measured_hbm"] = bytes_gen / (out[k][0] * 1e-3) / 1e9 / peak
+        if k.startswith("fitness"):
+            rep[k]["frac_of_measured_hbm"] = (16 * W + 4) * P / (out[k][0] * 1e-3) / 1e9 / peak
     rep["copy_pop_d2d(torch)"]["GBs"] = 2 * 16 * W * P / (out["copy_pop_d2d(torch)"][0] * 1e-3) / 1e9
     print(json.dumps({"workload": args.workload, "P": P, "W": W, "ops": rep}, indent=1))
 

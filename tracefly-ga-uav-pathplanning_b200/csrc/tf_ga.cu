@@ -35,7 +35,8 @@ ga_step_kernel(const V4* __restrict__ pop, const int32_t* __restrict__ lens, con
             V4* dst = next + (size_t)(slot0 + c) * W;
             // child = first[:cp] + second[cp:] (Python slicing): n1 waypoints of `first`, then `second` from index cp
             // on — the same index k unless cp exceeds len(first), which only a PF tape can ask for (PF:197-199)
-            const int n1 = uniform ? 0 : min(b.cp, lens ? lens[b.first] : W);
+            // (cp >= W — elite slots carry cp = 511 — copies the whole row of `first`, padding included)
+            const int n1 = uniform ? 0 : (b.cp >= W ? W : min(b.cp, lens ? lens[b.first] : W));
             for (int k = lane, s = 0; k < W; k += 32, ++s) {
                 V4 v;
                 if (uniform) {
