@@ -5,7 +5,14 @@
 
 namespace tf {
 
-constexpr int kStages = 6;
+// Row buffers per warp (the two-chromosome schedule uses them as kStages / 2 pair stages).  4, not more: shared
+// memory comes out of the same 256 KB as L1, and the voxel probes live on L1 — with 6 buffers (4 CTAs x 50 KB) the
+// SM keeps 28 KB of L1 and a spread-out population thrashes it; with 4 (4 x 33 KB) it keeps 92 KB.  cfg3 generation
+// kernel, generations 5..24: 0.421 ms with 6, 0.375 ms with 4, 0.418 ms with 2 (TF_STAGES is the A/B knob).
+#ifndef TF_STAGES
+#define TF_STAGES 4
+#endif
+constexpr int kStages = TF_STAGES;
 
 __host__ __device__ inline size_t stream_smem_bytes(const EnvDev& e, int W) {
     size_t tables = (smem_bytes_for(e) + 127) & ~(size_t)127;
