@@ -272,6 +272,9 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 // TF_DUO_XF1_CTAS is an A/B knob for build.py (TF_NVCC_EXTRA).
 // RAGW: the row length is a runtime value Wr <= 32 NW (any chromosome length up to 64 on the TMA-staged path);
 // lanes whose waypoint index is >= Wr are masked.  RAGW = false: W = 32 NW, the code of the BASELINE configs.
+#ifndef TF_PROBE_FIRST
+#define TF_PROBE_FIRST 1
+#endif
 template <int NW, int SEM, bool VOX, int XF, bool GA, bool RAGW>
 #ifndef TF_DUO_XF1_CTAS
 #define TF_DUO_XF1_CTAS 3
@@ -396,32 +399,49 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
                 }
                 __syncwarp();
             }
-            // segment sums first (length, altitude, turns: they only need the row), so that the neighbour
+            // per-lane partials of virtual lanes h (even m) and h + 16 (odd m), accumulated in waypoint order.
+            // XF 1: segment sums first (length, altitude, turns: they only need the row), so that the neighbour
             // waypoints are dead before the gather-heavy part (voxels, moving spheres, hazard map) starts.
-            // per-lane partials of virtual lanes h (even m) and h + 16 (odd m), accumulated in waypoint order
+            // XF 0 with a voxel grid: the probes go out FIRST and the segment sums (4 square roots per lane) run
+            // under their latency — the probe is the one long-latency load of the step and its words are only
+            // needed by the ballots at the end.
+            constexpr bool kProbeFirst = VOX && XF == 0 && (TF_PROBE_FIRST != 0);
             Lanes<NL> cur;
             float a_prox[2] = {0.0f, 0.0f}, a_dist[2] = {0.0f, 0.0f}, a_alt[2] = {0.0f, 0.0f}, a_haz[2] = {0.0f, 0.0f};
             int turns = 0, ncoll = 0;
             float4* dst = GA ? next + (size_t)(slot0 + half * hT + j) * W : nullptr;
-#pragma unroll
-            for (int m = 0; m < NL; ++m) {
-                const int k = h + 16 * m, v = m & 1;
+            auto fetch = [&](int m) {     // waypoint h + 16 m: into registers and out to the child row
+                const int k = h + 16 * m;
                 const bool ok = !RAGW || k < W;   // masked lanes sit at (-1, -1, -1): outside every grid
                 const float4 c4 = ok ? row[k] : make_float4(-1.0f, -1.0f, -1.0f, 0.0f);
-                const float4 q = ok ? row[k > 0 ? k - 1 : 0] : c4;
                 cur.x[m] = c4.x; cur.y[m] = c4.y; cur.z[m] = c4.z;
                 if constexpr (GA) {
                     if (live && ok) stg_stream_hint(dst + k, c4, pol_stream);
                 }
+            };
+            auto segment = [&](int m) {   // segment (k - 1, k)
+                const int k = h + 16 * m, v = m & 1;
+                const bool ok = !RAGW || k < W;
                 if (ok && (m > 0 || h > 0)) {  // k >= 1
-                    const float dx = c4.x - q.x, dy = c4.y - q.y, dz = c4.z - q.z;
+                    const float4 q = row[k - 1];
+                    const float dx = cur.x[m] - q.x, dy = cur.y[m] - q.y, dz = cur.z[m] - q.z;
                     a_dist[v] = __fadd_rn(a_dist[v], sqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
                     a_alt[v] = __fadd_rn(a_alt[v], fabsf(dz));                      // HR:44
-                    if (RAGW ? k <= W - 2 : (m < NL - 1 || h < 15)) turns += (c4.x != q.x || c4.y != q.y) ? 1 : 0;  // k <= W-2, HR:38-40,43
+                    if (RAGW ? k <= W - 2 : (m < NL - 1 || h < 15)) turns += (cur.x[m] != q.x || cur.y[m] != q.y) ? 1 : 0;  // k <= W-2, HR:38-40,43
                 }
-            }
+            };
             VoxRegs<NL> vr;
-            if constexpr (VOX) voxel_prefetch<NL>(e, cur, vr, pol_keep);
+            if constexpr (kProbeFirst) {
+#pragma unroll
+                for (int m = 0; m < NL; ++m) fetch(m);
+                voxel_prefetch<NL>(e, cur, vr, pol_keep);
+#pragma unroll
+                for (int m = 0; m < NL; ++m) segment(m);
+            } else {
+#pragma unroll
+                for (int m = 0; m < NL; ++m) { fetch(m); segment(m); }
+                if constexpr (VOX) voxel_prefetch<NL>(e, cur, vr, pol_keep);
+            }
             PointAcc<NL, SEM> acc;
             acc.reset();
             if constexpr (SEM != TF_SEM_NONE) eval_static<SEM, NL>(e, tabs, cur.x, cur.y, cur.z, acc.hit, acc.best);
