@@ -22,8 +22,8 @@ Workloads (BASELINE.json configs; synthetic, seeded, generated on the device):
 Inputs are far larger than L2 (population 1 GiB, ping-ponged between two buffers; grid 128 MiB).
 
 The ONE JSON line is the selected workload (default cfg3).  On top of the contract keys it carries
-  "workloads": short timed runs of the other BASELINE configs (N = 1: cfg1, cfg2, cfg4; N > 1: cfg5), each with its
-               own roofline and cpu_baseline,
+  "workloads": short timed runs of the other BASELINE configs (N = 1: cfg1, cfg2, cfg4, cfg5's per-GPU size; N > 1:
+               cfg5), each with its own roofline and cpu_baseline (cfg5 shares cfg3's world: no CPU legs of its own),
   "parity_gate": the correctness gate run with every benchmark (GPU vs oracle on a sample of the timed run's own
                population: fitness and collision flags bit-exact in the FP32 model, parents / crossover points /
                children bit-exact; N > 1: a small island world over NCCL vs the CPU restatement),
@@ -718,8 +718,10 @@ def summarize_workload(res, cpu_ref, cpu_port, gate):
     if cpu_ref:
         out["cpu_baseline"] = cpu_ref
         out["cpu_baseline_port"] = cpu_port
-    else:
+    elif cpu_port:
         out["cpu_baseline"] = cpu_port
+    else:
+        out["cpu_baseline"] = {"see": "the cfg3 line: same world, same operators, only the population size differs"}
     return out
 
 
@@ -767,7 +769,8 @@ def run_gpu(args):
     extras = {}
     if not args.no_extras:
         k, w = min(args.steps, 20), min(args.warmup, 5)
-        names = [n for n in (("cfg2", "cfg4") if ctx.world == 1 else ("cfg5",)) if n != name]
+        # cfg5's per-GPU size also at N = 1: the driver's 1/2/4/8 runs then hold a weak-scaling curve of cfg5 itself
+        names = [n for n in (("cfg2", "cfg4", "cfg5") if ctx.world == 1 else ("cfg5",)) if n != name]
         for n2 in names:
             env = params = ga = None
             torch.cuda.empty_cache()
@@ -781,7 +784,7 @@ def run_gpu(args):
             torch.cuda.empty_cache()
             if ctx.rank == 0:
                 cref = cport = None
-                if ctx.world == 1 and not args.no_cpu:
+                if ctx.world == 1 and not args.no_cpu and n2 != "cfg5":   # cfg5 = cfg3's world and operators: its CPU legs are cfg3's
                     cport = cpu_baseline_port(n2, seconds=3.0)
                     cref = cpu_baseline_reference(n2, steps=1)
                 extras[n2] = summarize_workload(r2, cref, cport, g2)
