@@ -251,6 +251,17 @@ int tf_generation(const tf_env* env, const float* pop_dev, const float* fit_dev,
                   const tf_ga_params* ga, const tf_params* params, int P, int W,
                   float* next_pop_dev, float* next_fit_dev, uint32_t* next_coll_dev,
                   int32_t* sel_dev, int32_t* cp_dev, void* stream);
+/* tf_generation followed by the ranking of its children: next_top_dev i32[next_k] = what
+ * tf_rank_topk(next_fit_dev, P, next_k, worst = 0) returns, i.e. the top_idx of the NEXT generation (HR:114 runs once
+ * per generation; this removes its launch from the generation loop).  Fused into the persistent generation kernel for
+ * next_k <= 2 on large populations (every warp keeps its two best children, the last warp of the grid merges them); any
+ * other case runs tf_rank_topk behind the generation — same result.  workspace: tf_topk_workspace_bytes(P, next_k, 0). */
+int tf_generation_ranked(const tf_env* env, const float* pop_dev, const float* fit_dev,
+                         const int32_t* top_idx_dev, const tf_draw* tape_dev, uint64_t seed, uint32_t generation,
+                         const tf_ga_params* ga, const tf_params* params, int P, int W,
+                         float* next_pop_dev, float* next_fit_dev, uint32_t* next_coll_dev,
+                         int32_t* sel_dev, int32_t* cp_dev, int32_t* next_top_dev, int next_k,
+                         void* workspace_dev, int64_t workspace_bytes, void* stream);
 
 /* HR:126-128 best tracking: if fit[slot] > *best_fit then { *best_fit = fit[slot];
  * best_path <- pop[slot]; *best_gen = generation }. */

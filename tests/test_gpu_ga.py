@@ -163,6 +163,39 @@ def test_fused_generation_equals_unfused_and_oracle(tf, combo, sem, W, N):
     assert np.array_equal(ofit, fit_f.cpu().numpy()) and np.array_equal(ocoll, as_u32(coll_f))
 
 
+@pytest.mark.parametrize("P,W,k,world", [(400_000, 64, 2, "voxel"), (400_000, 64, 1, "voxel"), (400_000, 48, 2, "empty"),
+                                          (400_000, 64, 3, "voxel"), (3001, 32, 2, "table"), (600_000, 32, 2, "flat")])
+def test_generation_ranked_returns_the_ranking_of_the_children(tf, P, W, k, world):
+    """tf_generation_ranked: next_top == tf_rank_topk(next_fit, k) == the oracle's stable order, whether the ranking
+    is fused into the persistent kernel (large P, k <= 2), runs behind it (k = 3, small P, obstacle table), and when
+    nearly all children tie ("flat": identical chromosomes, no mutation -> index order decides); and the generation
+    itself is unchanged by it."""
+    torch, L, B = tf
+    rng = np.random.default_rng(P + W + k)
+    if world == "table":
+        env = B.Environment(L.SEM_PF, random_table(rng, 40, 64, sem_pf=True), 0.0)
+    else:
+        env = B.Environment.empty()
+    if world == "voxel":
+        env.set_voxels(B.voxelize(random_table(rng, 300, 64, sem_pf=True), (64, 64, 64), L.SEM_PF), (64, 64, 64))
+    if world == "flat":
+        pop = B.init_diagonal((0, 0, 0), (W - 1, 0, 0), P, W=W)[0]
+    else:
+        pop = B.init_walks(5, P, W, start=(32, 32, 32), lo=(0, 0, 0), hi=(63, 63, 63))
+    prm = L.default_params(dist_zero_guard=0 if world == "table" else 1)
+    fit, _ = B.fitness_batch(pop, None, env, prm)
+    ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=3, mutation_rate=0.0 if world == "flat" else 0.2, n_elite=2)
+    top = B.rank_topk(fit, 2)
+    plan = B.TopK(P, k)
+    ntop = torch.full((k,), -1, dtype=torch.int32, device="cuda")
+    for rep in range(2):     # twice: the launch counters and the workspace are handed back clean
+        nxt, nfit, *_ = B.generation(env, pop, fit, top, ga, prm, seed=3, generation=rep, next_top=ntop, topk=plan)
+        ref_nxt, ref_fit, *_ = B.generation(env, pop, fit, top, ga, prm, seed=3, generation=rep)
+        assert torch.equal(nxt, ref_nxt) and torch.equal(nfit, ref_fit)
+        assert torch.equal(ntop, B.rank_topk(nfit, k))
+        assert np.array_equal(ntop.cpu().numpy(), O.topk(nfit.cpu().numpy(), k))
+
+
 def test_track_best_lag_quirk(tf):
     """HR:126-128: best follows population[0] (last generation's elite) with a strict '>'."""
     torch, L, B = tf

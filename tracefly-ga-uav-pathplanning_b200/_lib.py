@@ -78,6 +78,8 @@ _SIGS = {
     "tf_np_hr_tape": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp]),
     "tf_generation": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(GaParams), C.POINTER(Params), _i, _i,
                            _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tf_generation_ranked": (_i, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(GaParams), C.POINTER(Params), _i, _i,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i64, _vp]),
     "tf_track_best": (_i, [_vp, _vp, _i, _i, _u32, _vp, _vp, _vp, _vp]),
     "tf_track_best_f64": (_i, [_vp, _vp, _i, _i, _u32, _vp, _vp, _vp, _vp]),
     "tf_init_diagonal": (_i, [C.POINTER(_d), C.POINTER(_d), _i, _i, _vp, C.POINTER(_i), _vp]),

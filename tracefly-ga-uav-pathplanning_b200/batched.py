@@ -464,9 +464,11 @@ def ga_step(pop, fit, top_idx, ga=None, tape=None, seed=0, generation=0, lens=No
 
 
 def generation(env, pop, fit, top_idx, ga=None, params=None, tape=None, seed=0, generation=0, out_pop=None,
-               out_fit=None, want_collisions=False, want_parity=False):
+               out_fit=None, want_collisions=False, want_parity=False, next_top=None, topk=None):
     """Fused GA step + fitness sweep (FP32, fixed W): the child never round-trips through HBM.
-    -> (next_pop, next_fit, next_coll or None, sel or None, cp or None)"""
+    -> (next_pop, next_fit, next_coll or None, sel or None, cp or None)
+    next_top (i32[k], with topk = the TopK plan that owns the workspace): also filled with the ranking of the
+    children — rank_topk(next_fit, k) — so the generation loop needs no ranking launch (tf_generation_ranked)."""
     ga = ga or L.default_ga_params()
     _chk_tensor(pop, torch.float32, "pop", 3)
     P, W, _ = pop.shape
@@ -479,9 +481,16 @@ def generation(env, pop, fit, top_idx, ga=None, params=None, tape=None, seed=0, 
     coll = torch.empty((P, (W + 31) // 32), dtype=torch.int32, device=pop.device) if want_collisions else None
     sel = torch.empty((npairs, 2), dtype=torch.int32, device=pop.device) if want_parity else None
     cp = torch.empty(npairs, dtype=torch.int32, device=pop.device) if want_parity else None
-    rc = lib.tf_generation(env.handle, _ptr(pop), _ptr(fit), _ptr(top_idx), _ptr(tape), seed, generation,
-                           C.byref(ga), C.byref(params), P, W, _ptr(nxt), _ptr(nfit), _ptr(coll), _ptr(sel), _ptr(cp),
-                           _stream())
+    if next_top is not None:
+        if topk is None or topk.f64 or topk.P != P or next_top.numel() != topk.k:
+            raise ValueError("generation(next_top=...) needs topk = TopK(P, len(next_top))")
+        rc = lib.tf_generation_ranked(env.handle, _ptr(pop), _ptr(fit), _ptr(top_idx), _ptr(tape), seed, generation,
+                                      C.byref(ga), C.byref(params), P, W, _ptr(nxt), _ptr(nfit), _ptr(coll), _ptr(sel),
+                                      _ptr(cp), _ptr(next_top), topk.k, _ptr(topk.ws), topk.nbytes, _stream())
+    else:
+        rc = lib.tf_generation(env.handle, _ptr(pop), _ptr(fit), _ptr(top_idx), _ptr(tape), seed, generation,
+                               C.byref(ga), C.byref(params), P, W, _ptr(nxt), _ptr(nfit), _ptr(coll), _ptr(sel), _ptr(cp),
+                               _stream())
     if rc == L.TF_ERR_UNSUPPORTED:
         # more than 2048 analytic obstacles without a candidate index: the fused kernel stages one table chunk only.
         # The unfused pair gives the same results (tf_ga_step + tf_fitness walk the table in chunks).
@@ -489,6 +498,8 @@ def generation(env, pop, fit, top_idx, ga=None, params=None, tape=None, seed=0, 
                              _ptr(nxt), None, _ptr(sel), _ptr(cp), _stream()), "tf_ga_step")
         check(lib.tf_fitness(env.handle, _ptr(nxt), None, P, W, C.byref(params), _ptr(nfit), _ptr(coll), _stream()),
               "tf_fitness")
+        if next_top is not None:
+            topk(nfit, out=next_top)
         return nxt, nfit, coll, sel, cp
     check(rc, "tf_generation")
     return nxt, nfit, coll, sel, cp

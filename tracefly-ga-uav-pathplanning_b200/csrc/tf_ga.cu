@@ -231,10 +231,14 @@ extern "C" int tf_ga_step_f64(const double* pop64_dev, const int32_t* lens_dev, 
                                                 (cudaStream_t)stream);
 }
 
-extern "C" int tf_generation(const tf_env* env, const float* pop_dev, const float* fit_dev, const int32_t* top_idx_dev,
-                             const tf_draw* tape_dev, uint64_t seed, uint32_t generation, const tf_ga_params* ga,
-                             const tf_params* params, int P, int W, float* next_pop_dev, float* next_fit_dev,
-                             uint32_t* next_coll_dev, int32_t* sel_dev, int32_t* cp_dev, void* stream) {
+// tf_generation / tf_generation_ranked.  With next_top_dev the ranking of the CHILDREN (tf_rank_topk of next_fit_dev,
+// next_k best) is part of the call: fused into the persistent generation kernel where that kernel runs (the last warp
+// of the grid merges per-CTA candidates), a tf_rank_topk launch behind the generation otherwise.
+static int run_generation(const tf_env* env, const float* pop_dev, const float* fit_dev, const int32_t* top_idx_dev,
+                          const tf_draw* tape_dev, uint64_t seed, uint32_t generation, const tf_ga_params* ga,
+                          const tf_params* params, int P, int W, float* next_pop_dev, float* next_fit_dev,
+                          uint32_t* next_coll_dev, int32_t* sel_dev, int32_t* cp_dev, int32_t* next_top_dev, int next_k,
+                          void* ws, int64_t ws_bytes, void* stream) {
     if (!env || !pop_dev || !ga || !params || !next_pop_dev || !next_fit_dev || !top_idx_dev) return TF_ERR_INVALID;
     if (ga->selection == TF_SEL_TOURNAMENT && !tape_dev && !fit_dev) return TF_ERR_INVALID;
     if (P < 1 || W < 1 || W > TF_W_MAX) return TF_ERR_SHAPE;
@@ -243,20 +247,52 @@ extern "C" int tf_generation(const tf_env* env, const float* pop_dev, const floa
     if (ga->selection == TF_SEL_TRUNCATION && (ga->n_top < 2 || P < 2)) return TF_ERR_SHAPE;
     if (env->d.n_smem > kTableCap) return TF_ERR_UNSUPPORTED;  // use tf_ga_step + tf_fitness (same results)
     if (params->samples_per_segment > 64) return TF_ERR_SHAPE;
+    if (next_top_dev) {
+        if (next_k < 1 || next_k > TF_TOPK_MAX || next_k > P) return TF_ERR_SHAPE;
+        if (!ws || ws_bytes < tf_topk_workspace_bytes(P, next_k, 0)) return TF_ERR_WORKSPACE;
+    }
     int rc = ensure_device();
     if (rc != TF_OK) return rc;
+    bool ranked = false;
     if (stream_eligible(env->d, *params, W, ga->crossover == TF_CX_UNIFORM && tape_dev == nullptr) && !g_disable_stream) {
         StreamArgs sa{&env->d, params, ga, pop_dev, fit_dev, top_idx_dev, tape_dev, seed, generation, P, W,
                       next_pop_dev, next_fit_dev, next_coll_dev, sel_dev, cp_dev, (cudaStream_t)stream};
-        return generation_stream(sa);
+        if (next_top_dev) {
+            sa.next_top = next_top_dev;
+            sa.next_k = next_k;
+            sa.rank_part = reinterpret_cast<unsigned long long*>(((uintptr_t)ws + 15) & ~(uintptr_t)15);
+            sa.rank_part_bytes = ws_bytes - 16;
+        }
+        rc = generation_stream(sa);
+        ranked = sa.ranked;
+    } else {
+        GenArgs a{&env->d, params, ga, pop_dev, fit_dev, top_idx_dev, tape_dev, seed, generation, P, W,
+                  next_pop_dev, next_fit_dev, next_coll_dev, sel_dev, cp_dev, (cudaStream_t)stream};
+        const int nw = (W + 31) / 32;
+        rc = nw <= 1 ? generation_lsu_nw1(a) : nw <= 2 ? generation_lsu_nw2(a) : nw <= 4 ? generation_lsu_nw4(a) : generation_lsu_nw8(a);
     }
-    GenArgs a{&env->d, params, ga, pop_dev, fit_dev, top_idx_dev, tape_dev, seed, generation, P, W,
-              next_pop_dev, next_fit_dev, next_coll_dev, sel_dev, cp_dev, (cudaStream_t)stream};
-    const int nw = (W + 31) / 32;
-    if (nw <= 1) return generation_lsu_nw1(a);
-    if (nw <= 2) return generation_lsu_nw2(a);
-    if (nw <= 4) return generation_lsu_nw4(a);
-    return generation_lsu_nw8(a);
+    if (rc != TF_OK || !next_top_dev || ranked) return rc;
+    return tf_rank_topk(next_fit_dev, P, next_k, 0, next_top_dev, ws, ws_bytes, stream);
+}
+
+extern "C" int tf_generation(const tf_env* env, const float* pop_dev, const float* fit_dev, const int32_t* top_idx_dev,
+                             const tf_draw* tape_dev, uint64_t seed, uint32_t generation, const tf_ga_params* ga,
+                             const tf_params* params, int P, int W, float* next_pop_dev, float* next_fit_dev,
+                             uint32_t* next_coll_dev, int32_t* sel_dev, int32_t* cp_dev, void* stream) {
+    return run_generation(env, pop_dev, fit_dev, top_idx_dev, tape_dev, seed, generation, ga, params, P, W, next_pop_dev,
+                          next_fit_dev, next_coll_dev, sel_dev, cp_dev, nullptr, 0, nullptr, 0, stream);
+}
+
+extern "C" int tf_generation_ranked(const tf_env* env, const float* pop_dev, const float* fit_dev,
+                                    const int32_t* top_idx_dev, const tf_draw* tape_dev, uint64_t seed,
+                                    uint32_t generation, const tf_ga_params* ga, const tf_params* params, int P, int W,
+                                    float* next_pop_dev, float* next_fit_dev, uint32_t* next_coll_dev, int32_t* sel_dev,
+                                    int32_t* cp_dev, int32_t* next_top_dev, int next_k, void* workspace_dev,
+                                    int64_t workspace_bytes, void* stream) {
+    if (!next_top_dev) return TF_ERR_INVALID;
+    return run_generation(env, pop_dev, fit_dev, top_idx_dev, tape_dev, seed, generation, ga, params, P, W, next_pop_dev,
+                          next_fit_dev, next_coll_dev, sel_dev, cp_dev, next_top_dev, next_k, workspace_dev,
+                          workspace_bytes, stream);
 }
 
 extern "C" int tf_track_best(const float* pop_dev, const float* fit_dev, int slot, int W, uint32_t generation,

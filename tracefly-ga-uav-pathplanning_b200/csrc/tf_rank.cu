@@ -11,10 +11,7 @@ namespace tf {
 struct Key32 {  // fitness f32: one u64 = (~orderable(f) << 32) | idx
     unsigned long long v;
     __device__ __forceinline__ static Key32 make(float f, uint32_t idx, bool worst) {
-        if (f == 0.0f) f = 0.0f;  // -0.0 == +0.0 for Python's comparison
-        uint32_t u = __float_as_uint(f);
-        u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;  // ascending u <=> ascending f
-        unsigned long long k = ((unsigned long long)(~u) << 32) | idx;
+        const unsigned long long k = rank_key32(f, idx);  // -0.0 == +0.0 for Python's comparison
         return Key32{worst ? ~k : k};
     }
     __device__ __forceinline__ static Key32 pad() { return Key32{~0ull}; }

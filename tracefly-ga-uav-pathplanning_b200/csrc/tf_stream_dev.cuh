@@ -286,7 +286,7 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
            const tf_draw* __restrict__ tape, uint64_t seed, uint32_t gen, int P, int T,
            float4* __restrict__ next, float* __restrict__ out_fit, uint32_t* __restrict__ out_coll,
            int32_t* __restrict__ sel, int32_t* __restrict__ cpo, int n_big, int n_tickets, int* __restrict__ sched,
-           int Wr) {
+           int Wr, unsigned long long* __restrict__ rank_part, int32_t* __restrict__ next_top, int next_k) {
     constexpr int NL = 2 * NW, kPairStages = kStages / 2;
     const int W = RAGW ? Wr : 32 * NW;
     extern __shared__ __align__(128) unsigned char smem_stream[];
@@ -298,11 +298,18 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
     float4* ring = reinterpret_cast<float4*>(smem + tables) + (size_t)warp * kStages * W;   // kPairStages x 2 rows
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tables + (size_t)kWarpsPerBlock * kStages * W * 16) + warp * kStages;
     const int ne = GA ? min(ga.n_elite, P) : 0;
+    // fused ranking (GA, next_k = 1 or 2, dynamic schedule): the best keys this warp has produced so far, and the
+    // CTA's count of warps that ran dry — behind the mbarriers
+    unsigned long long* wbest = reinterpret_cast<unsigned long long*>(bars - warp * kStages + kWarpsPerBlock * kStages) + warp * 2;
+    unsigned int* cta_done = reinterpret_cast<unsigned int*>(wbest - warp * 2 + kWarpsPerBlock * 2);
+    const bool ranking = GA && next_k > 0;
 
     if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < kPairStages; ++i) mbar_init(&bars[i], 2);   // one arrival per half
+        if (ranking) { wbest[0] = ~0ull; wbest[1] = ~0ull; }
     }
+    if (ranking && threadIdx.x == 0) *cta_done = 0u;
     if ((SEM != TF_SEM_NONE && e.n_smem > 0) || (XF >= 1 && e.n_dyn_smem > 0)) {
         if (threadIdx.x == 0) mbar_init(sm.bar, 1);
         fence_mbar_init();
@@ -312,7 +319,8 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
         mbar_wait(sm.bar, 0);
     } else {
         fence_mbar_init();
-        __syncwarp();
+        if (ranking) __syncthreads();   // the CTA's counter is zeroed before any warp can run dry
+        else __syncwarp();
     }
 
     int head = 0;
@@ -533,9 +541,12 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
             head = next_stage(head);
         }
         // ---- phase C (lane = child of the tile)
+        unsigned long long key = ~0ull;
         if (own) {
             const int slot = slot0 + myc;
-            out_fit[slot] = combine_fitness<NW, XF>(e, prm, sums);
+            const float f = combine_fitness<NW, XF>(e, prm, sums);
+            out_fit[slot] = f;
+            if (ranking) key = rank_key32(f, (uint32_t)slot);
             if (out_coll) {
                 const int nwords = RAGW ? (W + 31) >> 5 : NW;   // the flag array is [P][ceil(W / 32)]
 #pragma unroll
@@ -543,13 +554,71 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
                     if (s < nwords) out_coll[(size_t)slot * nwords + s] = sums.cw[s];
             }
         }
+        if constexpr (GA) {
+            if (ranking) {   // children that beat the warp's next_k-th best so far: rare after the first tiles
+                unsigned int cand = __ballot_sync(0xffffffffu, key < wbest[next_k - 1]);
+                while (cand) {
+                    const unsigned long long k = __shfl_sync(0xffffffffu, key, __ffs(cand) - 1);
+                    cand &= cand - 1u;
+                    if (lane == 0) {
+                        const unsigned long long a = wbest[0], b = wbest[1];
+                        if (k < a) { wbest[0] = k; wbest[1] = a; }
+                        else if (k < b) wbest[1] = k;
+                    }
+                }
+                __syncwarp();
+            }
+        }
         ticket = dynamic ? __shfl_sync(0xffffffffu, ahead, 0) : ahead;
     }
-    // the last warp of the grid to run dry hands the counters back zeroed for the next launch
-    if (dynamic && lane == 0) {
-        if (atomicAdd(sched + 1, 1) == (int)(gridDim.x * kWarpsPerBlock) - 1) {
-            sched[0] = 0;
-            sched[1] = 0;
+    // fused ranking, step 2: the last warp of a CTA to run dry merges the CTA's 8 x 2 keys into rank_part
+    if constexpr (GA) {
+        if (ranking) {
+            __threadfence_block();
+            unsigned int nth = 0;
+            if (lane == 0) nth = atomicAdd(cta_done, 1u);
+            if (__shfl_sync(0xffffffffu, nth, 0) == (unsigned int)kWarpsPerBlock - 1u) {
+                __threadfence_block();
+                const unsigned long long* all = wbest - warp * 2;
+                unsigned long long a = ~0ull, b = ~0ull, first, second;
+                if (lane < kWarpsPerBlock) { a = all[2 * lane]; b = all[2 * lane + 1]; }
+                warp_two_smallest(a, b, first, second);
+                if (lane == 0) {
+                    rank_part[2 * blockIdx.x] = first;
+                    rank_part[2 * blockIdx.x + 1] = second;
+                    __threadfence();
+                }
+            }
+            __syncwarp();
+        }
+    }
+    // the last warp of the grid to run dry hands the counters back zeroed for the next launch — and, step 3 of the
+    // fused ranking, merges the CTAs' keys (every CTA wrote its pair before its last warp counted itself here)
+    if (dynamic) {
+        int last = 0;
+        if (lane == 0) last = atomicAdd(sched + 1, 1) == (int)(gridDim.x * kWarpsPerBlock) - 1;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            if constexpr (GA) {
+                if (ranking) {
+                    __threadfence();
+                    unsigned long long a = ~0ull, b = ~0ull, first, second;
+                    for (unsigned int i = lane; i < 2u * gridDim.x; i += 32u) {
+                        const unsigned long long k = __ldcg(rank_part + i);
+                        if (k < a) { b = a; a = k; }
+                        else if (k < b) b = k;
+                    }
+                    warp_two_smallest(a, b, first, second);
+                    if (lane == 0) {
+                        next_top[0] = (int32_t)(uint32_t)first;
+                        if (next_k > 1) next_top[1] = (int32_t)(uint32_t)second;
+                    }
+                }
+            }
+            if (lane == 0) {
+                sched[0] = 0;
+                sched[1] = 0;
+            }
         }
     }
 }
@@ -588,11 +657,15 @@ static int launch_duo(const StreamArgs& a, size_t smem, int T) {
         const int reserve = max(g_reserve_sms, (GA && a.ga) ? a.ga->reserve_sms : 0);
         grid = max(sm_count() - max(reserve, 0), sm_count() / 2) * max(occ, 1);
     }
+    // fused ranking of the children: only on the persistent grid (its last warp is the one that merges)
+    const bool rank = GA && sched != nullptr && a.next_top != nullptr && (a.next_k == 1 || a.next_k == 2) &&
+                      a.rank_part != nullptr && a.rank_part_bytes >= (int64_t)grid * 16 && a.P >= a.next_k;
     kern<<<grid, kBlockThreads, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
                                               a.top_idx, a.tape, a.seed, a.gen, a.P, T,
                                               reinterpret_cast<float4*>(a.next), a.out_fit, a.out_coll, a.sel, a.cpo,
-                                              n_big, n_big + n_small, sched, a.W);
+                                              n_big, n_big + n_small, sched, a.W, a.rank_part, a.next_top, rank ? a.next_k : 0);
     TF_LAUNCH_CHECK();
+    a.ranked = rank;
     return TF_OK;
 }
 

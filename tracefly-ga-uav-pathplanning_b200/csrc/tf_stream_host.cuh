@@ -16,13 +16,19 @@ constexpr int kStages = TF_STAGES;
 
 __host__ __device__ inline size_t stream_smem_bytes(const EnvDev& e, int W) {
     size_t tables = (smem_bytes_for(e) + 127) & ~(size_t)127;
-    return tables + (size_t)kWarpsPerBlock * kStages * W * 16 + (size_t)kWarpsPerBlock * kStages * 8;
+    // tables | row ring | mbarriers | fused ranking: two best keys per warp + the CTA's finished-warp counter
+    return tables + (size_t)kWarpsPerBlock * kStages * W * 16 + (size_t)kWarpsPerBlock * kStages * 8 +
+           (size_t)kWarpsPerBlock * 16 + 16;
 }
 
 struct StreamArgs {
     const EnvDev* e; const tf_params* prm; const tf_ga_params* ga; const float* pop; const float* fit;
     const int32_t* top_idx; const tf_draw* tape; uint64_t seed; uint32_t gen; int P, W;
     float* next; float* out_fit; uint32_t* out_coll; int32_t* sel; int32_t* cpo; cudaStream_t st;
+    // fused ranking of the children (tf_generation_ranked): the kernel writes the next_k (1 or 2) best slots of
+    // out_fit to next_top; rank_part = scratch for 2 keys per CTA; `ranked` is set by the launcher that did it
+    int32_t* next_top = nullptr; int next_k = 0; unsigned long long* rank_part = nullptr; int64_t rank_part_bytes = 0;
+    mutable bool ranked = false;
 };
 
 struct GenArgs {

@@ -51,7 +51,9 @@ class CudaOps:
     def rank(self, fit, out):
         return self.topk_rank(fit, out=out)
 
-    def generation(self, pop, fit, top, ga, seed, gen, out_pop, out_fit, beside_exchange=False):
+    fused_rank = True   # generation(next_top=...) also ranks the children (tf_generation_ranked)
+
+    def generation(self, pop, fit, top, ga, seed, gen, out_pop, out_fit, beside_exchange=False, next_top=None):
         # while an elite exchange is in flight on the side stream, the persistent generation kernel leaves a
         # few SMs free for it (it would otherwise hold every CTA slot until it ends).  The number travels in
         # the launch's own tf_ga_params copy: no library-wide state is touched.
@@ -63,7 +65,7 @@ class CudaOps:
             self._ga_beside.reserve_sms = self.reserve_sms
             ga = self._ga_beside
         self.B.generation(self.env, pop, fit, top, ga, self.params, seed=seed, generation=gen, out_pop=out_pop,
-                          out_fit=out_fit)
+                          out_fit=out_fit, next_top=next_top, topk=self.topk_rank if next_top is not None else None)
 
     def elites(self, fit, out):
         return self.best_set(fit, worst=False, out=out)
@@ -117,6 +119,11 @@ class IslandGA:
         self.nfit = torch.empty_like(self.fit)
         dev = pop.device
         self.top = torch.empty(self.k_rank, dtype=torch.int32, device=dev)
+        # the generation kernel ranks its own children (ops.fused_rank): `ntop` receives the next generation's top_idx
+        # and `_top_valid` says that `top` already ranks the current population (false at the start and after foreign
+        # elites were written into it)
+        self.ntop = torch.empty_like(self.top) if getattr(ops, "fused_rank", False) else None
+        self._top_valid = False
         self.gen = 0
         self.hook = None
         self.migrations = 0
@@ -135,7 +142,8 @@ class IslandGA:
         """rank -> select/crossover/mutate + fitness (fused); then the migration schedule.
         `self.hook`, if set, is called as hook("generation_begin" | "generation_end", self) right around the
         launch of the generation kernel (bench.py records its CUDA events there)."""
-        self.ops.rank(self.fit, self.top)
+        if not self._top_valid:
+            self.ops.rank(self.fit, self.top)
         if self.hook is not None:
             self.hook("generation_begin", self)
         self.launch_generation()
@@ -143,16 +151,18 @@ class IslandGA:
             self.hook("generation_end", self)
         self.pop, self.nxt = self.nxt, self.pop
         self.fit, self.nfit = self.nfit, self.fit
+        if self.ntop is not None:
+            self.top, self.ntop = self.ntop, self.top
+            self._top_valid = True
         self.gen += 1
         self.after_generation()
 
     def launch_generation(self):
         """The fused generation kernel of the current population into the spare buffers."""
+        kw = {"next_top": self.ntop} if self.ntop is not None else {}
         if self._pending and isinstance(self.ops, CudaOps):
-            self.ops.generation(self.pop, self.fit, self.top, self.ga, self.seed, self.gen, self.nxt, self.nfit,
-                                beside_exchange=True)
-        else:
-            self.ops.generation(self.pop, self.fit, self.top, self.ga, self.seed, self.gen, self.nxt, self.nfit)
+            kw["beside_exchange"] = True
+        self.ops.generation(self.pop, self.fit, self.top, self.ga, self.seed, self.gen, self.nxt, self.nfit, **kw)
 
     def after_generation(self):
         if self.world <= 1 or self.E == 0 or self.interval <= 0:
@@ -185,6 +195,7 @@ class IslandGA:
             self.ops.join_side_stream()
         self.ops.worst(self.fit, self.worst_idx)
         self.ops.replace(self.pop, self.fit, self.worst_idx, self.recv_rows, self.recv_fit, self.world, self.rank, self.E)
+        self._top_valid = False       # foreign elites may outrank the local best
         self._pending = False
         self.migrations += 1
 
