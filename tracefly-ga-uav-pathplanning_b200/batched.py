@@ -584,10 +584,15 @@ def evolve_batch(pop, env, generations, ga=None, params=None, seed=0, tapes=None
         tapes = torch.from_numpy(np.ascontiguousarray(tapes, np.int32)).to(pop.device)
     hist_best = torch.empty(generations, dtype=fit.dtype, device=pop.device) if history else None
     hist_mean = torch.empty(generations, dtype=fit.dtype, device=pop.device) if history else None
+    # the fused f32 generation ranks its own children (tf_generation_ranked): one ranking launch before the first
+    # generation, none inside the loop
+    ranked_gen = fused and not f64
+    ntop = torch.empty_like(top) if ranked_gen else None
     for g in range(generations):
         if should_stop is not None and should_stop():
             return None
-        topk(fit, out=top)
+        if g == 0 or not ranked_gen:
+            topk(fit, out=top)
         tape = None if tapes is None else tapes[g]
         gen_no = start_generation + g
         if f64 or not fused:
@@ -597,7 +602,9 @@ def evolve_batch(pop, env, generations, ga=None, params=None, seed=0, tapes=None
             else:
                 fitness_batch(nxt, None, env, params, out=nfit, want_collisions=False)
         else:
-            generation(env, cur, fit, top, ga, params, tape=tape, seed=seed, generation=gen_no, out_pop=nxt, out_fit=nfit)
+            generation(env, cur, fit, top, ga, params, tape=tape, seed=seed, generation=gen_no, out_pop=nxt, out_fit=nfit,
+                       next_top=ntop, topk=topk)
+            top, ntop = ntop, top
         cur, nxt = nxt, cur
         fit, nfit = nfit, fit
         if tracker is not None:
