@@ -164,7 +164,7 @@ def test_fused_generation_equals_unfused_and_oracle(tf, combo, sem, W, N):
 
 
 @pytest.mark.parametrize("P,W,k,world", [(400_000, 64, 2, "voxel"), (400_000, 64, 1, "voxel"), (400_000, 48, 2, "empty"),
-                                          (400_000, 64, 3, "voxel"), (3001, 32, 2, "table"), (600_000, 32, 2, "flat")])
+                                          (400_000, 64, 3, "voxel"), (3001, 32, 2, "table"), (65_536, 32, 2, "table"), (65_536, 64, 1, "table"), (600_000, 32, 2, "flat")])
 def test_generation_ranked_returns_the_ranking_of_the_children(tf, P, W, k, world):
     """tf_generation_ranked: next_top == tf_rank_topk(next_fit, k) == the oracle's stable order, whether the ranking
     is fused into the persistent kernel (large P, k <= 2), runs behind it (k = 3, small P, obstacle table), and when

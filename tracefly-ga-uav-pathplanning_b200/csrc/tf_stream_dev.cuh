@@ -21,6 +21,60 @@
 
 namespace tf {
 
+// ---- fused ranking of the children (tf_generation_ranked): HR:114 sorts once per generation; here the generation
+// kernel keeps the next_k (1 or 2) best ranking keys of the children it writes.  wbest: two keys per warp in shared
+// memory; cta_done: the CTA's count of warps that ran dry; rank_part: one pair of keys per CTA in global memory.
+// A warp notes the keys of a tile (one per owning lane, ~0 for lanes without a child): a ballot finds the rare
+// child that beats the warp's next_k-th best so far.
+__device__ __forceinline__ void rank_note(unsigned long long key, unsigned long long* wbest, int next_k, int lane) {
+    unsigned int cand = __ballot_sync(0xffffffffu, key < wbest[next_k - 1]);
+    while (cand) {
+        const unsigned long long k = __shfl_sync(0xffffffffu, key, __ffs(cand) - 1);
+        cand &= cand - 1u;
+        if (lane == 0) {
+            const unsigned long long a = wbest[0], b = wbest[1];
+            if (k < a) { wbest[0] = k; wbest[1] = a; }
+            else if (k < b) wbest[1] = k;
+        }
+    }
+    __syncwarp();
+}
+// Called by every warp when it has run dry: the last one of the CTA merges the CTA's 8 x 2 keys into rank_part.
+__device__ __forceinline__ void rank_merge_cta(const unsigned long long* wbest_all, unsigned int* cta_done,
+                                               unsigned long long* __restrict__ rank_part, int lane) {
+    __threadfence_block();
+    unsigned int nth = 0;
+    if (lane == 0) nth = atomicAdd(cta_done, 1u);
+    if (__shfl_sync(0xffffffffu, nth, 0) == (unsigned int)kWarpsPerBlock - 1u) {
+        __threadfence_block();
+        unsigned long long a = ~0ull, b = ~0ull, first, second;
+        if (lane < kWarpsPerBlock) { a = wbest_all[2 * lane]; b = wbest_all[2 * lane + 1]; }
+        warp_two_smallest(a, b, first, second);
+        if (lane == 0) {
+            rank_part[2 * blockIdx.x] = first;
+            rank_part[2 * blockIdx.x + 1] = second;
+            __threadfence();
+        }
+    }
+    __syncwarp();
+}
+// Called by the last warp of the GRID to run dry (every CTA wrote its pair before its last warp counted itself).
+__device__ __forceinline__ void rank_merge_grid(const unsigned long long* __restrict__ rank_part, int32_t* __restrict__ next_top,
+                                                int next_k, int lane) {
+    __threadfence();
+    unsigned long long a = ~0ull, b = ~0ull, first, second;
+    for (unsigned int i = lane; i < 2u * gridDim.x; i += 32u) {
+        const unsigned long long k = __ldcg(rank_part + i);
+        if (k < a) { b = a; a = k; }
+        else if (k < b) b = k;
+    }
+    warp_two_smallest(a, b, first, second);
+    if (lane == 0) {
+        next_top[0] = (int32_t)(uint32_t)first;
+        if (next_k > 1) next_top[1] = (int32_t)(uint32_t)second;
+    }
+}
+
 // Score bookkeeping of one full-length chromosome whose waypoints sit in shared memory.
 template <int NW, int SEM, bool VOX, int XF>
 __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& prm, const Tables& t,
@@ -555,65 +609,22 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
             }
         }
         if constexpr (GA) {
-            if (ranking) {   // children that beat the warp's next_k-th best so far: rare after the first tiles
-                unsigned int cand = __ballot_sync(0xffffffffu, key < wbest[next_k - 1]);
-                while (cand) {
-                    const unsigned long long k = __shfl_sync(0xffffffffu, key, __ffs(cand) - 1);
-                    cand &= cand - 1u;
-                    if (lane == 0) {
-                        const unsigned long long a = wbest[0], b = wbest[1];
-                        if (k < a) { wbest[0] = k; wbest[1] = a; }
-                        else if (k < b) wbest[1] = k;
-                    }
-                }
-                __syncwarp();
-            }
+            if (ranking) rank_note(key, wbest, next_k, lane);
         }
         ticket = dynamic ? __shfl_sync(0xffffffffu, ahead, 0) : ahead;
     }
-    // fused ranking, step 2: the last warp of a CTA to run dry merges the CTA's 8 x 2 keys into rank_part
     if constexpr (GA) {
-        if (ranking) {
-            __threadfence_block();
-            unsigned int nth = 0;
-            if (lane == 0) nth = atomicAdd(cta_done, 1u);
-            if (__shfl_sync(0xffffffffu, nth, 0) == (unsigned int)kWarpsPerBlock - 1u) {
-                __threadfence_block();
-                const unsigned long long* all = wbest - warp * 2;
-                unsigned long long a = ~0ull, b = ~0ull, first, second;
-                if (lane < kWarpsPerBlock) { a = all[2 * lane]; b = all[2 * lane + 1]; }
-                warp_two_smallest(a, b, first, second);
-                if (lane == 0) {
-                    rank_part[2 * blockIdx.x] = first;
-                    rank_part[2 * blockIdx.x + 1] = second;
-                    __threadfence();
-                }
-            }
-            __syncwarp();
-        }
+        if (ranking) rank_merge_cta(wbest - warp * 2, cta_done, rank_part, lane);
     }
-    // the last warp of the grid to run dry hands the counters back zeroed for the next launch — and, step 3 of the
-    // fused ranking, merges the CTAs' keys (every CTA wrote its pair before its last warp counted itself here)
+    // the last warp of the grid to run dry hands the counters back zeroed for the next launch and merges the CTAs'
+    // ranking keys
     if (dynamic) {
         int last = 0;
         if (lane == 0) last = atomicAdd(sched + 1, 1) == (int)(gridDim.x * kWarpsPerBlock) - 1;
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {
             if constexpr (GA) {
-                if (ranking) {
-                    __threadfence();
-                    unsigned long long a = ~0ull, b = ~0ull, first, second;
-                    for (unsigned int i = lane; i < 2u * gridDim.x; i += 32u) {
-                        const unsigned long long k = __ldcg(rank_part + i);
-                        if (k < a) { b = a; a = k; }
-                        else if (k < b) b = k;
-                    }
-                    warp_two_smallest(a, b, first, second);
-                    if (lane == 0) {
-                        next_top[0] = (int32_t)(uint32_t)first;
-                        if (next_k > 1) next_top[1] = (int32_t)(uint32_t)second;
-                    }
-                }
+                if (ranking) rank_merge_grid(rank_part, next_top, next_k, lane);
             }
             if (lane == 0) {
                 sched[0] = 0;
@@ -682,6 +693,9 @@ static int launch_stream(const StreamArgs& a) {
         if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int ntiles = (a.P + T - 1) / T;
         const int grid = min((ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
+        // (no fused ranking here: the ranking state costs this kernel 16 registers — 80 instead of 64, 3 instead
+        // of 4 CTAs / SM, cfg2 generation 61 -> 87 us — more than the 14 us ranking launch it would save;
+        // tf_generation_ranked runs tf_rank_topk behind these variants)
         kern<<<grid, kBlockThreads, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
                                                   a.top_idx, a.tape, a.seed, a.gen, a.P, T,
                                                   reinterpret_cast<float4*>(a.next), a.out_fit, a.out_coll, a.sel, a.cpo);
