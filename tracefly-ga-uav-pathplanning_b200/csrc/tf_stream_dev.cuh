@@ -329,6 +329,9 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 #ifndef TF_PROBE_FIRST
 #define TF_PROBE_FIRST 1
 #endif
+#ifndef TF_ROW_GATHER      // 0: the owning lane's two TMA bulk copies; 1: per-lane 16-byte cp.async (A/B experiment)
+#define TF_ROW_GATHER 0
+#endif
 template <int NW, int SEM, bool VOX, int XF, bool GA, bool RAGW>
 #ifndef TF_DUO_XF1_CTAS
 #define TF_DUO_XF1_CTAS 3
@@ -417,6 +420,28 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
         // pair j -> stage st: each owning lane gathers its own child's two parent pieces (or just arrives
         // when the pair has no second child)
         auto issue = [&](int j, int st) {
+#if TF_ROW_GATHER
+            // every lane copies its own waypoints of its half's child (16 bytes each, L1 bypassed) from whichever
+            // parent covers them; the child's plan comes from its owning lane by three shuffles
+            const int src_lane = (lane & 16) | j;
+            const int pfirst = __shfl_sync(0xffffffffu, mine.first, src_lane), psecond = __shfl_sync(0xffffffffu, mine.second, src_lane);
+            const int cpc = min(meta_cp(__shfl_sync(0xffffffffu, mine.meta, src_lane)), W);
+            const bool has = __shfl_sync(0xffffffffu, (int)own, src_lane) != 0;
+            if (has) {
+                const uint32_t dst = ring_u32 + (uint32_t)(st * 2 + half) * (W * 16u) + (uint32_t)h * 16u;
+                const float4* pa = pop + (size_t)pfirst * W + h;
+                const float4* pb = pop + (size_t)psecond * W + h;
+#pragma unroll
+                for (int m = 0; m < NL; ++m) {
+                    const int k = h + 16 * m;
+                    if (RAGW && k >= W) continue;
+                    const float4* src = (k < cpc ? pa : pb) + 16 * m;
+                    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)m * 256u), "l"(src), "l"(pol_stream) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            return;
+#endif
             if (h == j) {
                 const uint32_t bar = bars_u32 + (uint32_t)st * 8u;
                 if (own) {
@@ -439,15 +464,28 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
         const int npairs = min(cnt, hT);
         {
             int st = head;
+#if TF_ROW_GATHER
+            for (int j = 0; j < kPairStages; ++j) {   // one group per stage, empty past the end of the tile
+                if (j < npairs) issue(j, st);
+                else asm volatile("cp.async.commit_group;" ::: "memory");
+                st = next_stage(st);
+            }
+#else
             for (int j = 0; j < min(npairs, kPairStages); ++j) { issue(j, st); st = next_stage(st); }
+#endif
         }
 #pragma unroll 1
         for (int j = 0; j < npairs; ++j) {
             const bool hasB = hT + j < cnt;                       // warp-uniform
             const bool live = half == 0 || hasB;                  // this half has a chromosome of its own
             float4* row = ring + (head * 2 + (hasB ? half : 0)) * W;
+#if TF_ROW_GATHER
+            asm volatile("cp.async.wait_group %0;" ::"n"(kPairStages - 1) : "memory");   // pair j's group has landed
+            __syncwarp();
+#else
             mbar_wait(&bars[head], (phase >> head) & 1u);
             phase ^= 1u << head;
+#endif
             if constexpr (GA) {
                 if (h == j && own) {  // the owning lane applies its child's mutation (HR:97-98)
                     const int mp = meta_mp(mine.meta);
@@ -592,6 +630,9 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
             }
             __syncwarp();  // every lane is done with this stage: refill it
             if (j + kPairStages < npairs) issue(j + kPairStages, head);
+#if TF_ROW_GATHER
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
             head = next_stage(head);
         }
         // ---- phase C (lane = child of the tile)
