@@ -110,7 +110,7 @@ def workload_label(name, cfg, P):
 
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons sampled DURING the timed region through NVML (the same counters
-    nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.* prints), every 5 ms."""
+    nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.* prints), every millisecond."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
@@ -140,7 +140,7 @@ class ClockSampler(threading.Thread):
                 self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def finish(self):
         self.stop_flag = True
@@ -302,6 +302,7 @@ def time_generations(ctx, name, cfg, steps, warmup):
     gen_times = [a.elapsed_time(b) for a, b in gen_ev]
     step_times = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(steps)]
     gen_ms = float(np.mean(gen_times))
+    gen_ms_slowest = ctx.max_over_ranks(gen_ms)    # the islands meet at every exchange: the slowest GPU sets the pace
     q = max(1, len(gen_times) // 4)
     units_per_step = ctx.world * P * (W - 1)
     peak, peak_src = measured_peak_gbs()
@@ -325,7 +326,7 @@ def time_generations(ctx, name, cfg, steps, warmup):
                      "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bpu * P * (W - 1), "algorithmic_bytes_per_unit": bpu, "kernel_ms": gen_ms,
                      "kernel_ms_first_quarter": float(np.mean(gen_times[:q])), "kernel_ms_last_quarter": float(np.mean(gen_times[-q:])),
-                     "kernel_share_of_step": gen_ms / (ms_total / steps)},
+                     "kernel_share_of_step": gen_ms / (ms_total / steps), "kernel_ms_slowest_rank": gen_ms_slowest},
         "clocks": clocks, "gpu_launches": int(launches),
     }
     if os.environ.get("TF_BENCH_TRACE"):

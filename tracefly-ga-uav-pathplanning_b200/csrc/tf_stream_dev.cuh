@@ -700,7 +700,10 @@ static int launch_duo(const StreamArgs& a, size_t smem, int T) {
     int grid = min((n_big + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
     if (T >= 8 && a.P / T >= 4 * resident_warps) {
         const int Ts = T >> 1;
-        n_big = (GA && XF == 0) ? 0 : (a.P - 2 * resident_warps * Ts) / T;
+#ifndef TF_GA_TAIL_TILES   // A/B: 0 = the plain fused generation runs on half-size tiles only; n = tiles of T with n half-size tiles per resident warp at the end
+#define TF_GA_TAIL_TILES 0
+#endif
+        n_big = (GA && XF == 0 && TF_GA_TAIL_TILES == 0) ? 0 : (a.P - max(TF_GA_TAIL_TILES, 2) * resident_warps * Ts) / T;
         n_small = (a.P - n_big * T + Ts - 1) / Ts;
         sched = sched_slot();
         if (sched == nullptr) return TF_ERR_NOMEM;
