@@ -257,6 +257,8 @@ def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind, P):
         g.manual_seed(W)
         pop[..., :3] += torch.rand(pop[..., :3].shape, device="cuda", generator=g) * 0.75 - 0.25
     ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=3, mutation_rate=0.5, n_elite=3)
+    gau = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=3, crossover=L.CX_UNIFORM, mutation=L.MUT_GAUSSIAN,
+                              mutation_rate=0.5, sigma=0.75, n_elite=3)
     res = []
     for disable, schedule in ((0, 0), (0, 1), (0, 2), (1, 0)):
         L.set_option(L.OPT_DISABLE_STREAM, disable)
@@ -265,8 +267,10 @@ def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind, P):
             fit, coll = B.fitness_batch(pop, None, env, prm)
             top = B.rank_topk(fit, 3)
             out = B.generation(env, pop, fit, top, ga, prm, seed=77, generation=9, want_collisions=True, want_parity=True)
+            # uniform crossover + Gaussian mutation: both parent rows staged (stream_kernel<..., UX>) for W = 32 / 64
+            uni = B.generation(env, pop, fit, top, gau, prm, seed=78, generation=4, want_collisions=True, want_parity=True)
             torch.cuda.synchronize()
-            res.append((fit, coll) + out)
+            res.append((fit, coll) + out + uni)
         finally:
             L.set_option(L.OPT_DISABLE_STREAM, 0)
             L.set_option(L.OPT_STREAM_SCHEDULE, 0)

@@ -65,12 +65,12 @@ def main():
     out["sum_pop(torch.sum, read only)"] = timeit(torch, lambda: torch.sum(pop))
     src = torch.empty_like(pop)
     out["copy_pop_d2d(torch)"] = timeit(torch, lambda: src.copy_(pop))
-    # ---- the variants that stay on the LSU path (tf_stream_host.cuh: stream_eligible): uniform crossover, S > 1
-    #      samples per segment, ragged lengths — north_star names the first two; their roofline fractions
+    # ---- the north-star-named variants and the ones that stay on the LSU path (tf_stream_host.cuh: stream_eligible:
+    #      S > 1 samples per segment, ragged lengths); their roofline fractions
     peak = bench.measured_peak_gbs()[0]
     gau = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=4, crossover=L.CX_UNIFORM, mutation=L.MUT_GAUSSIAN,
                               mutation_rate=0.1, sigma=1.5, n_elite=2)
-    out["generation_fused_uniform_crossover_gaussian_mutation(LSU path)"] = timeit(
+    out["generation_fused_uniform_crossover_gaussian_mutation(TMA path, both parent rows staged)"] = timeit(
         torch, lambda: B.generation(env, pop, fit, top, gau, params, seed=1, generation=1, out_pop=nxt, out_fit=nfit))
     gam = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=4, mutation=L.MUT_GAUSSIAN, mutation_rate=0.1, sigma=1.5, n_elite=2)
     out["generation_fused_single_point_gaussian_mutation(TMA path)"] = timeit(

@@ -254,9 +254,11 @@ static int run_generation(const tf_env* env, const float* pop_dev, const float* 
     int rc = ensure_device();
     if (rc != TF_OK) return rc;
     bool ranked = false;
-    if (stream_eligible(env->d, *params, W, ga->crossover == TF_CX_UNIFORM && tape_dev == nullptr) && !g_disable_stream) {
+    const bool uniform = ga->crossover == TF_CX_UNIFORM && tape_dev == nullptr;
+    if (stream_eligible(env->d, *params, W, uniform) && !g_disable_stream) {
         StreamArgs sa{&env->d, params, ga, pop_dev, fit_dev, top_idx_dev, tape_dev, seed, generation, P, W,
                       next_pop_dev, next_fit_dev, next_coll_dev, sel_dev, cp_dev, (cudaStream_t)stream};
+        sa.uniform = uniform;
         if (next_top_dev) {
             sa.next_top = next_top_dev;
             sa.next_k = next_k;

@@ -149,7 +149,11 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
 
 // GA = true : fused generation (plan, gather both parents, mutate, store child, evaluate)
 // GA = false: fitness sweep (row p, no store)
-template <int NW, int SEM, bool VOX, int XF, bool GA>
+// UX = true : uniform crossover (north-star extension).  A child takes every waypoint from one of its two parents by a
+//             Philox mask, so BOTH parent rows are staged — a child occupies two ring slots (the ring holds 2 children
+//             instead of 4) — and the lanes move the masked waypoints of the second row into the first before the
+//             mutation; from there on the slot is read exactly like a single-point child.
+template <int NW, int SEM, bool VOX, int XF, bool GA, bool UX = false>
 __global__ void __launch_bounds__(kBlockThreads, (XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? 3 : 0))
 // 32 warps / SM for the HBM-bound plain variant (<= 64 registers), 24 for the gather-heavy XF 1
 // variants (<= 80); the obstacle-loop (FP32-bound) and sampling variants are left to ptxas
@@ -161,6 +165,8 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
               float4* __restrict__ next, float* __restrict__ out_fit, uint32_t* __restrict__ out_coll,
               int32_t* __restrict__ sel, int32_t* __restrict__ cpo) {
     constexpr int W = 32 * NW;
+    constexpr int kSl = UX ? 2 : 1, kSt = kStages / kSl;   // ring slots per child, children in flight
+    static_assert(!UX || GA, "uniform crossover exists only in the fused generation");
     extern __shared__ __align__(128) unsigned char smem_stream[];
     unsigned char* smem = smem_stream;
     const SmemLayout sm = carve_smem(e, smem);
@@ -193,7 +199,7 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
     uint32_t phase = 0;
     const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
     const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
-    auto next_slot = [](int st) { return st + 1 == kStages ? 0 : st + 1; };
+    auto next_slot = [](int st) { return st + 1 == kSt ? 0 : st + 1; };
 
     const int ntiles = (P + T - 1) / T;
     for (int tile = blockIdx.x * kWarpsPerBlock + warp; tile < ntiles; tile += gridDim.x * kWarpsPerBlock) {
@@ -213,24 +219,41 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
         // copies from its own plan registers (no broadcast of the plan to an elected lane)
         auto issue = [&](int c, int st) {
             if (lane == c) {
-                const int cpc = min(meta_cp(mine.meta), W);
-                const uint32_t dst = ring_u32 + (uint32_t)st * (W * 16u), bar = bars_u32 + (uint32_t)st * 8u;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)W * 16u) : "memory");
-                if (cpc > 0)
+                const uint32_t dst = ring_u32 + (uint32_t)(st * kSl) * (W * 16u), bar = bars_u32 + (uint32_t)st * 8u;
+                if constexpr (UX) {   // both parents, whole rows
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * W * 16u) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-                                 "l"(pop + (size_t)mine.first * W), "r"((uint32_t)cpc * 16u), "r"(bar), "l"(pol_stream) : "memory");
-                if (cpc < W)
+                                 "l"(pop + (size_t)mine.first * W), "r"((uint32_t)W * 16u), "r"(bar), "l"(pol_stream) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                                     dst + (uint32_t)cpc * 16u),
-                                 "l"(pop + (size_t)mine.second * W + cpc), "r"((uint32_t)(W - cpc) * 16u), "r"(bar), "l"(pol_stream) : "memory");
+                                     dst + (uint32_t)W * 16u),
+                                 "l"(pop + (size_t)mine.second * W), "r"((uint32_t)W * 16u), "r"(bar), "l"(pol_stream) : "memory");
+                } else {
+                    const int cpc = min(meta_cp(mine.meta), W);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)W * 16u) : "memory");
+                    if (cpc > 0)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                                     "l"(pop + (size_t)mine.first * W), "r"((uint32_t)cpc * 16u), "r"(bar), "l"(pol_stream) : "memory");
+                    if (cpc < W)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                                         dst + (uint32_t)cpc * 16u),
+                                     "l"(pop + (size_t)mine.second * W + cpc), "r"((uint32_t)(W - cpc) * 16u), "r"(bar), "l"(pol_stream) : "memory");
+                }
             }
         };
 
         // wait for child c's row (ring slot st), apply its mutation in shared memory, start its voxel gathers
         auto prepare = [&](int c, int st, uint32_t (&vword)[NW], uint32_t (&vmask)[NW]) {
-            float4* row = ring + st * W;
+            float4* row = ring + st * kSl * W;
             mbar_wait(&bars[st], (phase >> st) & 1u);
             phase ^= 1u << st;
+            if constexpr (UX) {   // masked waypoints come from the second parent (staged right behind the first)
+#pragma unroll
+                for (int s = 0; s < NW; ++s) {
+                    const uint32_t m = __shfl_sync(0xffffffffu, mine.mask[s], c);
+                    if ((m >> lane) & 1u) row[lane + 32 * s] = row[W + lane + 32 * s];
+                }
+                __syncwarp();
+            }
             if constexpr (GA) {
                 if (lane == c) {  // the owning lane applies its child's mutation (HR:97-98)
                     const int mp = meta_mp(mine.meta);
@@ -259,7 +282,7 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
         };
 
         // all ring slots are free at a tile boundary: slots head, head+1, ... take children 0, 1, ...
-        const int pre = min(cnt, kStages);
+        const int pre = min(cnt, kSt);
         {
             int st = head;
             for (int c = 0; c < pre; ++c) { issue(c, st); st = next_slot(st); }
@@ -272,7 +295,7 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
         for (int c = 0; c < cnt; ++c) {
             const int st_next = next_slot(head);
             if (c + 1 < cnt) prepare(c + 1, st_next, v1w, v1m);
-            const float4* row = ring + head * W;
+            const float4* row = ring + head * kSl * W;
             Lanes<NW> cur, prev;
             float4* dst = GA ? next + (size_t)(slot0 + c) * W : nullptr;
 #pragma unroll
@@ -289,7 +312,7 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
             if constexpr (SEM != TF_SEM_NONE) eval_static<SEM, NW>(e, tabs, cur.x, cur.y, cur.z, acc.hit, acc.best);
             reduce_fullw<NW, SEM, VOX, XF>(e, prm, tabs, cur, prev, v0w, v0m, acc, c, sums);
             __syncwarp();  // every lane is done with this ring slot: refill it
-            if (c + kStages < cnt) issue(c + kStages, head);
+            if (c + kSt < cnt) issue(c + kSt, head);
             head = st_next;
 #pragma unroll
             for (int s = 0; s < NW; ++s) { v0w[s] = v1w[s]; v0m[s] = v1m[s]; }
@@ -731,9 +754,12 @@ static int launch_stream(const StreamArgs& a) {
     // schedule: two chromosomes per warp step wherever there is no obstacle-table loop (measured faster on the
     // voxel / hazard / moving-sphere variants); with a table loop the extra registers (104 vs 64) halve the
     // occupancy and one chromosome per warp step stays ahead (cfg2: 56 us vs 71 us)
-    const bool duo = g_stream_schedule == 0 ? SEM == TF_SEM_NONE : g_stream_schedule == 2;
+    const bool duo = !a.uniform && (g_stream_schedule == 0 ? SEM == TF_SEM_NONE : g_stream_schedule == 2);
     if (!duo) {  // one chromosome per warp step, static tile assignment
         auto kern = stream_kernel<NW, SEM, VOX, XF, GA>;
+        if constexpr (GA) {
+            if (a.uniform) kern = stream_kernel<NW, SEM, VOX, XF, GA, true>;
+        }
         if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int ntiles = (a.P + T - 1) / T;
         const int grid = min((ntiles + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);

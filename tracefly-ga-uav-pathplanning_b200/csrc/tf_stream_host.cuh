@@ -29,6 +29,7 @@ struct StreamArgs {
     // out_fit to next_top; rank_part = scratch for 2 keys per CTA; `ranked` is set by the launcher that did it
     int32_t* next_top = nullptr; int next_k = 0; unsigned long long* rank_part = nullptr; int64_t rank_part_bytes = 0;
     mutable bool ranked = false;
+    bool uniform = false;   // uniform crossover from Philox masks: both parent rows are staged (stream_kernel<..., UX>)
 };
 
 struct GenArgs {
@@ -40,7 +41,8 @@ struct GenArgs {
 // Host-side eligibility: full-length chromosomes, single table chunk, contiguous parent pieces.
 inline bool stream_eligible(const EnvDev& e, const tf_params& prm, int W, bool uniform_mask) {
     if (prm.samples_per_segment > 1) return false;
-    if (uniform_mask || e.n_smem > kTableCap) return false;
+    if (e.n_smem > kTableCap) return false;
+    if (uniform_mask && W != 32 && W != 64) return false;   // the one-chromosome-per-step kernel: W = 32 NW exactly
     if (W != 32 && W != 64) {  // other lengths: the two-chromosome schedule with masked lanes, no table loop
         const bool table = e.n > 0 && e.semantics != TF_SEM_NONE;
         if (W < 3 || W > 256 || table || g_stream_schedule == 1) return false;
