@@ -1,6 +1,7 @@
 // tf_stream_dev.cuh — TMA-staged form of the FP32 fitness sweep / fused generation for fixed-length
-// chromosomes (no ragged lengths, no uniform crossover), in two warp schedules:
-//   stream_kernel  one chromosome per warp step; W = 32 NW exactly (W = 32, 64); the variants WITH an obstacle table;
+// chromosomes (no ragged lengths), in two warp schedules:
+//   stream_kernel  one chromosome per warp step; W = 32 NW exactly (W = 32, 64); the variants WITH an obstacle table,
+//                  and uniform crossover (UX: both parent rows staged, two ring slots per child);
 //   duo_kernel     two chromosomes per warp step (one per half-warp), dynamic tile tickets; the variants WITHOUT a
 //                  table; runtime row length (3 <= W <= 256, masked lanes) on top of the exact-W form.
 //

@@ -38,7 +38,8 @@ struct GenArgs {
     float* next; float* next_fit; uint32_t* next_coll; int32_t* sel; int32_t* cpo; cudaStream_t st;
 };
 
-// Host-side eligibility: full-length chromosomes, single table chunk, contiguous parent pieces.
+// Host-side eligibility: full-length chromosomes, single table chunk; parent pieces contiguous (single-point
+// crossover, any staged W) or whole rows (uniform crossover, W = 32 / 64).
 inline bool stream_eligible(const EnvDev& e, const tf_params& prm, int W, bool uniform_mask) {
     if (prm.samples_per_segment > 1) return false;
     if (e.n_smem > kTableCap) return false;
