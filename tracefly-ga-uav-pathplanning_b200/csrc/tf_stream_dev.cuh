@@ -356,6 +356,9 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 #ifndef TF_ROW_GATHER      // 0: the owning lane's two TMA bulk copies; 1: per-lane 16-byte cp.async (A/B experiment)
 #define TF_ROW_GATHER 0
 #endif
+#ifndef TF_GA_TAIL_TILES   // A/B: 0 = the plain fused generation runs on half-size tiles only; n = tiles of T with n
+#define TF_GA_TAIL_TILES 0 //      half-size tiles per resident warp at the end (re-measured with the 4-buffer ring: 0 wins)
+#endif
 template <int NW, int SEM, bool VOX, int XF, bool GA, bool RAGW>
 #ifndef TF_DUO_XF1_CTAS
 #define TF_DUO_XF1_CTAS 3
@@ -724,9 +727,6 @@ static int launch_duo(const StreamArgs& a, size_t smem, int T) {
     int grid = min((n_big + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
     if (T >= 8 && a.P / T >= 4 * resident_warps) {
         const int Ts = T >> 1;
-#ifndef TF_GA_TAIL_TILES   // A/B: 0 = the plain fused generation runs on half-size tiles only; n = tiles of T with n half-size tiles per resident warp at the end
-#define TF_GA_TAIL_TILES 0
-#endif
         n_big = (GA && XF == 0 && TF_GA_TAIL_TILES == 0) ? 0 : (a.P - max(TF_GA_TAIL_TILES, 2) * resident_warps * Ts) / T;
         n_small = (a.P - n_big * T + Ts - 1) / Ts;
         sched = sched_slot();
