@@ -251,6 +251,7 @@ def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind, P):
         env.set_dynamic(dyn, 1.0)
         env.set_hazard(torch.from_numpy(rng.uniform(0, 1, size=(8, 16, 16)).astype(np.float32)).cuda(), 0.25, 0.25, 0, 0, 7.0 / (W - 1))
     prm = L.default_params(hazard_weight=0.3)
+    prm3 = L.default_params(hazard_weight=0.3, samples_per_segment=3)
     pop = B.init_walks(5, P, W, start=(32, 32, 32), lo=(0, 0, 0), hi=(63, 63, 63))
     if P == 5003:   # off-lattice waypoints (what MAIN passes): fractional coordinates through the same kernels
         g = torch.Generator(device="cuda")
@@ -269,8 +270,12 @@ def test_tma_stream_kernels_equal_lsu_kernels(tf, W, env_kind, P):
             out = B.generation(env, pop, fit, top, ga, prm, seed=77, generation=9, want_collisions=True, want_parity=True)
             # uniform crossover + Gaussian mutation: both parent rows staged (stream_kernel<..., UX>) for W = 32 / 64
             uni = B.generation(env, pop, fit, top, gau, prm, seed=78, generation=4, want_collisions=True, want_parity=True)
+            # S = 3 samples per segment (XF 2: the one-chromosome-per-step TMA kernel for W = 32 / 64)
+            fit3, coll3 = B.fitness_batch(pop, None, env, prm3)
+            gen3 = B.generation(env, pop, fit3, B.rank_topk(fit3, 3), ga, prm3, seed=79, generation=2, want_collisions=True,
+                                want_parity=True)
             torch.cuda.synchronize()
-            res.append((fit, coll) + out + uni)
+            res.append((fit, coll) + out + uni + (fit3, coll3) + gen3)
         finally:
             L.set_option(L.OPT_DISABLE_STREAM, 0)
             L.set_option(L.OPT_STREAM_SCHEDULE, 0)

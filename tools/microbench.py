@@ -77,7 +77,7 @@ def main():
         torch, lambda: B.generation(env, pop, fit, top, gam, params, seed=1, generation=1, out_pop=nxt, out_fit=nfit))
     p3 = L.Params.from_buffer_copy(params)
     p3.samples_per_segment = 3
-    out["fitness_S3_samples_per_segment(LSU path)"] = timeit(torch, lambda: B.fitness_batch(pop, None, env, p3, out=fit, want_collisions=False), n=10)
+    out["fitness_S3_samples_per_segment(TMA path)"] = timeit(torch, lambda: B.fitness_batch(pop, None, env, p3, out=fit, want_collisions=False), n=10)
     lens = torch.full((P,), W, dtype=torch.int32, device="cuda")
     lens[::3] = W - 7
     out["fitness_ragged_lengths(LSU path)"] = timeit(torch, lambda: B.fitness_batch(pop, lens, env, params, out=fit, want_collisions=False))

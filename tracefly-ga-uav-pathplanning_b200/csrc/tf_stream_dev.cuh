@@ -1,7 +1,7 @@
 // tf_stream_dev.cuh — TMA-staged form of the FP32 fitness sweep / fused generation for fixed-length
 // chromosomes (no ragged lengths), in two warp schedules:
 //   stream_kernel  one chromosome per warp step; W = 32 NW exactly (W = 32, 64); the variants WITH an obstacle table,
-//                  and uniform crossover (UX: both parent rows staged, two ring slots per child);
+//                  uniform crossover (UX: both parent rows staged, two ring slots per child) and S > 1 samples (XF 2);
 //   duo_kernel     two chromosomes per warp step (one per half-warp), dynamic tile tickets; the variants WITHOUT a
 //                  table; runtime row length (3 <= W <= 256, masked lanes) on top of the exact-W form.
 //
@@ -755,10 +755,11 @@ static int launch_stream(const StreamArgs& a) {
     // schedule: two chromosomes per warp step wherever there is no obstacle-table loop (measured faster on the
     // voxel / hazard / moving-sphere variants); with a table loop the extra registers (104 vs 64) halve the
     // occupancy and one chromosome per warp step stays ahead (cfg2: 56 us vs 71 us)
-    const bool duo = !a.uniform && (g_stream_schedule == 0 ? SEM == TF_SEM_NONE : g_stream_schedule == 2);
+    // uniform crossover and S > 1 samples per segment (XF 2) exist in the one-chromosome-per-step kernel only
+    const bool duo = XF < 2 && !a.uniform && (g_stream_schedule == 0 ? SEM == TF_SEM_NONE : g_stream_schedule == 2);
     if (!duo) {  // one chromosome per warp step, static tile assignment
         auto kern = stream_kernel<NW, SEM, VOX, XF, GA>;
-        if constexpr (GA) {
+        if constexpr (GA && XF < 2) {
             if (a.uniform) kern = stream_kernel<NW, SEM, VOX, XF, GA, true>;
         }
         if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -773,17 +774,22 @@ static int launch_stream(const StreamArgs& a) {
         TF_LAUNCH_CHECK();
         return TF_OK;
     }
-    if (a.W != 32 * NW) {
-        if constexpr (SEM == TF_SEM_NONE) return launch_duo<NW, SEM, VOX, XF, GA, true>(a, smem, T);
-        else return TF_ERR_UNSUPPORTED;  // stream_eligible() never sends these here
+    if constexpr (XF < 2) {
+        if (a.W != 32 * NW) {
+            if constexpr (SEM == TF_SEM_NONE) return launch_duo<NW, SEM, VOX, XF, GA, true>(a, smem, T);
+            else return TF_ERR_UNSUPPORTED;  // stream_eligible() never sends these here
+        }
+        return launch_duo<NW, SEM, VOX, XF, GA, false>(a, smem, T);
+    } else {
+        return TF_ERR_UNSUPPORTED;
     }
-    return launch_duo<NW, SEM, VOX, XF, GA, false>(a, smem, T);
 }
 template <int NW, int SEM, bool GA>
 static int stream_flags(const StreamArgs& a) {
-    // XF 2 (samples per segment > 1) is served by the LSU-path kernels only (stream_eligible)
     const bool vox = a.e->bricks != nullptr;
     const bool xf1 = a.e->n_dyn > 0 || a.e->hazard != nullptr;
+    if (a.prm->samples_per_segment > 1)   // XF 2: the segment-sampling form (W = 32 / 64, no uniform crossover: stream_eligible)
+        return vox ? launch_stream<NW, SEM, true, 2, GA>(a) : launch_stream<NW, SEM, false, 2, GA>(a);
     if (vox) return xf1 ? launch_stream<NW, SEM, true, 1, GA>(a) : launch_stream<NW, SEM, true, 0, GA>(a);
     return xf1 ? launch_stream<NW, SEM, false, 1, GA>(a) : launch_stream<NW, SEM, false, 0, GA>(a);
 }

@@ -41,9 +41,10 @@ struct GenArgs {
 // Host-side eligibility: full-length chromosomes, single table chunk; parent pieces contiguous (single-point
 // crossover, any staged W) or whole rows (uniform crossover, W = 32 / 64).
 inline bool stream_eligible(const EnvDev& e, const tf_params& prm, int W, bool uniform_mask) {
-    if (prm.samples_per_segment > 1) return false;
     if (e.n_smem > kTableCap) return false;
-    if (uniform_mask && W != 32 && W != 64) return false;   // the one-chromosome-per-step kernel: W = 32 NW exactly
+    // uniform crossover / S > 1 samples per segment: the one-chromosome-per-step kernel, W = 32 NW exactly, not both
+    if ((uniform_mask || prm.samples_per_segment > 1) && W != 32 && W != 64) return false;
+    if (uniform_mask && prm.samples_per_segment > 1) return false;
     if (W != 32 && W != 64) {  // other lengths: the two-chromosome schedule with masked lanes, no table loop
         const bool table = e.n > 0 && e.semantics != TF_SEM_NONE;
         if (W < 3 || W > 256 || table || g_stream_schedule == 1) return false;
