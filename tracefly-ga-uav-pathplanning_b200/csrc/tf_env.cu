@@ -313,7 +313,9 @@ build_cyl_index_kernel(const __grid_constant__ EnvDev e, int nz, float oz, float
     if (threadIdx.x == 0) count[c] = n_list <= cap ? n_list : -1;
 }
 
-// [t][y][x] -> corner-packed [y][x][t]: (v[t][y][x], v[t][y][x1], v[t1][y][x], v[t1][y][x1]), x1 / t1 clamped
+// [t][y][x] -> corner-packed [y][x][t]: (v[t][y][x], v[t][y][x1] - v[t][y][x], v[t1][y][x], v[t1][y][x1] - v[t1][y][x]),
+// x1 / t1 clamped.  The x differences are the FP32 subtractions hazard_sample's lerp would do per sample (same
+// operands, same rounding): stored once, they turn its four x-lerps into single fmas.
 __global__ void hazard_pack_kernel(const float* __restrict__ in, float4* __restrict__ out, int nt, int ny, int nx) {
     const size_t nyx = (size_t)ny * nx, n = nyx * (size_t)nt;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -321,7 +323,8 @@ __global__ void hazard_pack_kernel(const float* __restrict__ in, float4* __restr
         const int t = (int)(i - c * nt), x = (int)(c % nx);
         const size_t c1 = x + 1 < nx ? c + 1 : c;
         const size_t t1 = t + 1 < nt ? t + 1 : t;
-        out[i] = make_float4(in[(size_t)t * nyx + c], in[(size_t)t * nyx + c1], in[t1 * nyx + c], in[t1 * nyx + c1]);
+        const float v00 = in[(size_t)t * nyx + c], v01 = in[(size_t)t * nyx + c1], v10 = in[t1 * nyx + c], v11 = in[t1 * nyx + c1];
+        out[i] = make_float4(v00, __fsub_rn(v01, v00), v10, __fsub_rn(v11, v10));
     }
 }
 

@@ -265,12 +265,12 @@ __device__ __forceinline__ void dyn_brute_force(const float4* __restrict__ dynA,
 // its record in drec); the entries come in groups {1..3}, {4..7}, {8..11}, ... and the last group of a list is
 // filled up with copies of its first entry (min / or are idempotent), so a group is walked without per-entry
 // predicates and its loads go out together.  Lists of up to 7 spheres need no second list load.
-__device__ __forceinline__ void dyn_group(const EnvDev& e, uint32_t w0, uint32_t w1, float x, float y, float z, float tm,
-                                          bool& h, float& m2) {
-    dyn_test_rec(e.drec, (int)(w0 & 0xffffu), x, y, z, tm, h, m2);
-    dyn_test_rec(e.drec, (int)(w0 >> 16), x, y, z, tm, h, m2);
-    dyn_test_rec(e.drec, (int)(w1 & 0xffffu), x, y, z, tm, h, m2);
-    dyn_test_rec(e.drec, (int)(w1 >> 16), x, y, z, tm, h, m2);
+__device__ __forceinline__ void dyn_group(const float4* __restrict__ drec, uint32_t w0, uint32_t w1, float x, float y, float z,
+                                          float tm, bool& h, float& m2) {
+    dyn_test_rec(drec, (int)(w0 & 0xffffu), x, y, z, tm, h, m2);
+    dyn_test_rec(drec, (int)(w0 >> 16), x, y, z, tm, h, m2);
+    dyn_test_rec(drec, (int)(w1 & 0xffffu), x, y, z, tm, h, m2);
+    dyn_test_rec(drec, (int)(w1 >> 16), x, y, z, tm, h, m2);
 }
 __device__ __forceinline__ void dyn_walk(const EnvDev& e, int cell, const uint4 hd, float x, float y, float z, int ti, bool& h,
                                          float& m2) {
@@ -282,14 +282,17 @@ __device__ __forceinline__ void dyn_walk(const EnvDev& e, int cell, const uint4 
             dyn_test_rec(e.drec, (int)(hd.y & 0xffffu), x, y, z, tm, h, m2);
             dyn_test_rec(e.drec, (int)(hd.y >> 16), x, y, z, tm, h, m2);
         }
-        if (n > 3) dyn_group(e, hd.z, hd.w, x, y, z, tm, h, m2);
+        if (n > 3) dyn_group(e.drec, hd.z, hd.w, x, y, z, tm, h, m2);
         if (n > 7) {
+            // (moving this rare tail and the brute-force fallback out of line shrinks the kernel by a third — it
+            // loses 8 % of its issue slots to instruction-cache misses — but the call's register saves cost more:
+            // cfg4 0.912 -> 0.989 ms)
             const uint4* list = reinterpret_cast<const uint4*>(e.dcand + (size_t)(uint32_t)cell * (uint32_t)e.dcap) + 1;
 #pragma unroll 1
             for (int j = 7; j < n; j += 8, ++list) {
                 const uint4 q = __ldg(list);
-                dyn_group(e, q.x, q.y, x, y, z, tm, h, m2);
-                if (j + 4 < n) dyn_group(e, q.z, q.w, x, y, z, tm, h, m2);
+                dyn_group(e.drec, q.x, q.y, x, y, z, tm, h, m2);
+                if (j + 4 < n) dyn_group(e.drec, q.z, q.w, x, y, z, tm, h, m2);
             }
         }
     } else {
@@ -405,14 +408,15 @@ __device__ __forceinline__ float hazard_sample(const EnvDev& e, float x, float y
     const int y1 = min(y0 + 1, e.hny - 1);
     const float fx = __fsub_rn(gx, (float)x0), fy = __fsub_rn(gy, (float)y0), ft = __fsub_rn(gt, (float)t0);
     // the env keeps the map corner-packed in [y][x][t] order: one float4 holds the (x0, x1) x (t0, t1) taps of
-    // a row y (clamping of x1 / t1 folded in at pack time), so the 8 taps are 2 loads; the lanes of a warp are
+    // a row y (clamping of x1 / t1 folded in at pack time; x1 as its difference to x0), so the 8 taps are 2 loads; the lanes of a warp are
     // consecutive waypoints, i.e. nearly the same (x, y) at consecutive times: their taps share cache lines.
     // 32-bit element indices (the packed map has < 2^29 elements)
     const uint32_t col = (uint32_t)(x0 * e.nt + t0), rowlen = (uint32_t)(e.hnx * e.nt);
     const float4 a = __ldg(e.hazard + ((uint32_t)y0 * rowlen + col));
     const float4 b = __ldg(e.hazard + ((uint32_t)y1 * rowlen + col));
-    const float a0 = lerp_f(lerp_f(a.x, a.y, fx), lerp_f(b.x, b.y, fx), fy);
-    const float a1 = lerp_f(lerp_f(a.z, a.w, fx), lerp_f(b.z, b.w, fx), fy);
+    // .y / .w hold the x differences (v[x1] - v[x0], subtracted in FP32 at pack time): lerp_f(v0, v1, fx) = fmaf(fx, v1 - v0, v0)
+    const float a0 = lerp_f(fmaf(fx, a.y, a.x), fmaf(fx, b.y, b.x), fy);
+    const float a1 = lerp_f(fmaf(fx, a.w, a.z), fmaf(fx, b.w, b.z), fy);
     return lerp_f(a0, a1, ft);
 }
 

@@ -353,7 +353,13 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 #ifndef TF_PROBE_FIRST
 #define TF_PROBE_FIRST 1
 #endif
-#ifndef TF_ROW_GATHER      // 0: the owning lane's two TMA bulk copies; 1: per-lane 16-byte cp.async (A/B experiment)
+// Row staging of duo_kernel: the owning lane's two TMA bulk copies, or — kGather — per-lane 16-byte cp.async copies
+// (every lane fetches its own waypoints from whichever parent covers them; the plan comes from the owning lane by three
+// shuffles).  Bit-identical.  Measured (round 2, same box, default run): cfg3 0.3757 -> 0.3733 ms, cfg4 0.9529 -> 0.9175 ms:
+// the hazard / moving-sphere variant (XF 1) is instruction-bound and short of registers (the TMA issue sequence costs 78
+// instructions per pair and 124 bytes of spills), so XF 1 gathers per lane; the plain variant keeps TMA.
+// TF_ROW_GATHER: 0 = that default, 1 = per-lane everywhere, -1 = TMA everywhere (A/B).
+#ifndef TF_ROW_GATHER
 #define TF_ROW_GATHER 0
 #endif
 #ifndef TF_GA_TAIL_TILES   // A/B: 0 = the plain fused generation runs on half-size tiles only; n = tiles of T with n
@@ -372,6 +378,7 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
            int32_t* __restrict__ sel, int32_t* __restrict__ cpo, int n_big, int n_tickets, int* __restrict__ sched,
            int Wr, unsigned long long* __restrict__ rank_part, int32_t* __restrict__ next_top, int next_k) {
     constexpr int NL = 2 * NW, kPairStages = kStages / 2;
+    constexpr bool kGather = TF_ROW_GATHER > 0 || (TF_ROW_GATHER == 0 && XF == 1);
     const int W = RAGW ? Wr : 32 * NW;
     extern __shared__ __align__(128) unsigned char smem_stream[];
     unsigned char* smem = smem_stream;
@@ -447,7 +454,7 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
         // pair j -> stage st: each owning lane gathers its own child's two parent pieces (or just arrives
         // when the pair has no second child)
         auto issue = [&](int j, int st) {
-#if TF_ROW_GATHER
+          if constexpr (kGather) {
             // every lane copies its own waypoints of its half's child (16 bytes each, L1 bypassed) from whichever
             // parent covers them; the child's plan comes from its owning lane by three shuffles
             const int src_lane = (lane & 16) | j;
@@ -467,8 +474,7 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            return;
-#endif
+          } else {
             if (h == j) {
                 const uint32_t bar = bars_u32 + (uint32_t)st * 8u;
                 if (own) {
@@ -486,33 +492,34 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
                 }
             }
+          }
         };
 
         const int npairs = min(cnt, hT);
         {
             int st = head;
-#if TF_ROW_GATHER
-            for (int j = 0; j < kPairStages; ++j) {   // one group per stage, empty past the end of the tile
-                if (j < npairs) issue(j, st);
-                else asm volatile("cp.async.commit_group;" ::: "memory");
-                st = next_stage(st);
+            if constexpr (kGather) {
+                for (int j = 0; j < kPairStages; ++j) {   // one group per stage, empty past the end of the tile
+                    if (j < npairs) issue(j, st);
+                    else asm volatile("cp.async.commit_group;" ::: "memory");
+                    st = next_stage(st);
+                }
+            } else {
+                for (int j = 0; j < min(npairs, kPairStages); ++j) { issue(j, st); st = next_stage(st); }
             }
-#else
-            for (int j = 0; j < min(npairs, kPairStages); ++j) { issue(j, st); st = next_stage(st); }
-#endif
         }
 #pragma unroll 1
         for (int j = 0; j < npairs; ++j) {
             const bool hasB = hT + j < cnt;                       // warp-uniform
             const bool live = half == 0 || hasB;                  // this half has a chromosome of its own
             float4* row = ring + (head * 2 + (hasB ? half : 0)) * W;
-#if TF_ROW_GATHER
-            asm volatile("cp.async.wait_group %0;" ::"n"(kPairStages - 1) : "memory");   // pair j's group has landed
-            __syncwarp();
-#else
-            mbar_wait(&bars[head], (phase >> head) & 1u);
-            phase ^= 1u << head;
-#endif
+            if constexpr (kGather) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(kPairStages - 1) : "memory");   // pair j's group has landed
+                __syncwarp();
+            } else {
+                mbar_wait(&bars[head], (phase >> head) & 1u);
+                phase ^= 1u << head;
+            }
             if constexpr (GA) {
                 if (h == j && own) {  // the owning lane applies its child's mutation (HR:97-98)
                     const int mp = meta_mp(mine.meta);
@@ -657,9 +664,7 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
             }
             __syncwarp();  // every lane is done with this stage: refill it
             if (j + kPairStages < npairs) issue(j + kPairStages, head);
-#if TF_ROW_GATHER
-            else asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
+            else if constexpr (kGather) asm volatile("cp.async.commit_group;" ::: "memory");
             head = next_stage(head);
         }
         // ---- phase C (lane = child of the tile)
