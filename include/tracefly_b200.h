@@ -376,6 +376,11 @@ void tf_philox4x32_10(uint32_t key0, uint32_t key1, uint32_t c0, uint32_t c1, ui
  * *mismatches_dev (u64, device, caller-zeroed) the number of bit patterns in [first_bits, first_bits + count)
  * whose result differs from sqrt.rn.f32.  count <= 2^32. */
 int tf_selftest_sqrt(uint32_t first_bits, uint64_t count, uint64_t* mismatches_dev, void* stream);
+/* Self-test of the library's FP32 reciprocal (MUFU.RCP seed + fma Newton step for 1 <= y < 2^126, div.rn elsewhere;
+ * the proximity term 1 / (1 + d) of HR:46 in the FP32 model): adds to *mismatches_dev the number of bit patterns y in
+ * [first_bits, first_bits + count) for which it differs from div.rn.f32(1, y) (each pattern is checked through the scalar
+ * and the batched form).  count <= 2^32. */
+int tf_selftest_rcp(uint32_t first_bits, uint64_t count, uint64_t* mismatches_dev, void* stream);
 /* Options.  TF_OPT_DISABLE_STREAM = 1 forces the LSU-path kernels even where the TMA-staged
  * kernels apply (fixed length W <= 256; with an obstacle table W = 32 / 64); both give bit-identical results. */
 #define TF_OPT_DISABLE_STREAM 1

@@ -299,3 +299,14 @@ def test_library_sqrt_is_correctly_rounded_for_every_float(tf):
         L.check(L.lib.tf_selftest_sqrt(first, 1 << 31, bad.data_ptr(), torch.cuda.current_stream().cuda_stream),
                 "tf_selftest_sqrt")
     assert int(bad.item()) == 0
+
+
+def test_library_reciprocal_is_correctly_rounded_for_every_float(tf):
+    """HR:46's 1 / (1 + d): the library's reciprocal (MUFU.RCP seed + fma Newton step for 1 <= y < 2^126, div.rn for
+    every other input) must equal div.rn.f32(1, y) for all 2^32 bit patterns, scalar and batched form."""
+    torch, L, B = tf
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for first in (0, 1 << 31):
+        L.check(L.lib.tf_selftest_rcp(first, 1 << 31, bad.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                "tf_selftest_rcp")
+    assert int(bad.item()) == 0

@@ -99,6 +99,7 @@ _SIGS = {
     "tf_pack_xyz": (_i, [_vp, _vp, _i64, _vp]),
     "tf_find_path_pf": (_i, [_vp, C.POINTER(_d), C.POINTER(_d), _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "tf_selftest_sqrt": (_i, [_u32, _u64, _vp, _vp]),
+    "tf_selftest_rcp": (_i, [_u32, _u64, _vp, _vp]),
     "tf_set_option": (_i, [_i, _i]),
     "tf_launch_count": (_i64, []),
 }

@@ -180,7 +180,9 @@ build_dyn_index_kernel(const float4* __restrict__ dynA, const float4* __restrict
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        cand[cellid * cap] = (uint16_t)(n_list <= cap - 1 ? n_list : 0xffff);
+        // (a list is never empty — the nearest sphere of every time slice is on it — and the walk relies on that: an
+        // empty one would be marked as overflowed)
+        cand[cellid * cap] = (uint16_t)(n_list >= 1 && n_list <= cap - 1 ? n_list : 0xffff);
         // the walk reads whole groups of entries ({1..3}, {4..7}, ...) without per-entry predicates: fill the last
         // group with copies of the first entry (min / or are idempotent)
         if (n_list > 0 && n_list <= cap - 1)
@@ -741,6 +743,32 @@ __global__ void selftest_sqrt_kernel(uint32_t lo, uint64_t n, unsigned long long
     if (mine) atomicAdd(bad, mine);
 }
 }  // namespace tf
+
+namespace tf {
+__global__ void selftest_rcp_kernel(uint32_t lo, uint64_t n, unsigned long long* bad) {
+    unsigned long long mine = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float y = __uint_as_float(lo + (uint32_t)i);
+        const float ys[2] = {y, 1.5f};
+        float rs[2];
+        rcp_rn_n<2>(ys, rs);
+        const uint32_t a = __float_as_uint(rcp_rn(y)), a2 = __float_as_uint(rs[0]), b = __float_as_uint(__fdiv_rn(1.0f, y));
+        const bool nan_b = isnan(__uint_as_float(b));
+        mine += (a != b && !(isnan(__uint_as_float(a)) && nan_b)) ? 1 : 0;
+        mine += (a2 != b && !(isnan(__uint_as_float(a2)) && nan_b)) ? 1 : 0;
+    }
+    if (mine) atomicAdd(bad, mine);
+}
+}  // namespace tf
+
+extern "C" int tf_selftest_rcp(uint32_t first_bits, uint64_t count, uint64_t* mismatches_dev, void* stream) {
+    if (!mismatches_dev || count > (1ull << 32)) return TF_ERR_INVALID;
+    if (count == 0) return TF_OK;
+    tf::selftest_rcp_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(first_bits, count,
+                                                                     (unsigned long long*)mismatches_dev);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
 
 extern "C" int tf_selftest_sqrt(uint32_t first_bits, uint64_t count, uint64_t* mismatches_dev, void* stream) {
     if (!mismatches_dev || count > (1ull << 32)) return TF_ERR_INVALID;

@@ -215,6 +215,9 @@ __device__ __forceinline__ void eval_static(const EnvDev& e, const Tables& t, co
     else eval_static_chunk<SEM, NP>(e, t, 0, min(e.n, kTableCap), x, y, z, hit, best);
 }
 
+#ifndef TF_DYN_PHASED   // A/B: 1 = eval_dynamic walks its NP candidate lists in phases (below), 0 = list by list
+#define TF_DYN_PHASED 1
+#endif
 // Moving spheres (extension): HR rules at c(t) = c0 + v t.  Returns min d^2 per point.
 // With a candidate index (tf_env_build_dynamic_index) a point at an integer time slice inside the
 // index box only visits the spheres listed for its cell — a superset of "nearest" and of "colliding"
@@ -327,6 +330,54 @@ __device__ __forceinline__ void eval_dynamic(const EnvDev& e, const Tables& t, c
         }
         return;
     }
+#if TF_DYN_PHASED
+    // Three phases, so that the common case is ONE straight-line block: (1) the cells and the first 8 bytes of the NP
+    // lists (length + entries 1..3) — NP independent loads in flight; (2) entries 1..3 of every list, unconditionally
+    // (an indexed list holds at least the nearest sphere and its first group is padded; a point outside the index and an
+    // overflowed list read (0xffff, 0): three tests against sphere 0, which the loop over all spheres repeats — min / or
+    // are idempotent); (3) behind one branch, the lists longer than three entries and the loop over all spheres.
+    int cell[NP];
+    uint2 hd[NP];
+#pragma unroll
+    for (int s = 0; s < NP; ++s) {
+        cell[s] = dyn_cell(e, x[s], y[s], z[s], t0 + dt * s);
+        hd[s] = make_uint2(0xffffu, 0u);
+        if (cell[s] >= 0) hd[s] = __ldg(reinterpret_cast<const uint2*>(e.dcand + (size_t)(uint32_t)cell[s] * (uint32_t)e.dcap));
+    }
+    bool rare = false;
+#pragma unroll
+    for (int s = 0; s < NP; ++s) {
+        const float tm = (float)(t0 + dt * s);
+        bool h = false;
+        dyn_test_rec(e.drec, (int)(hd[s].x >> 16), x[s], y[s], z[s], tm, h, m2[s]);
+        dyn_test_rec(e.drec, (int)(hd[s].y & 0xffffu), x[s], y[s], z[s], tm, h, m2[s]);
+        dyn_test_rec(e.drec, (int)(hd[s].y >> 16), x[s], y[s], z[s], tm, h, m2[s]);
+        hit |= h ? (1u << s) : 0u;
+        rare = rare || (hd[s].x & 0xffffu) > 3u;
+    }
+    if (rare) {
+#pragma unroll
+        for (int s = 0; s < NP; ++s) {
+            const int n = (int)(hd[s].x & 0xffffu);
+            if (n <= 3) continue;
+            const float tm = (float)(t0 + dt * s);
+            bool h = false;
+            if (n != 0xffff) {
+                const uint2* list = reinterpret_cast<const uint2*>(e.dcand + (size_t)(uint32_t)cell[s] * (uint32_t)e.dcap) + 1;
+                const uint2 g = __ldg(list);
+                dyn_group(e.drec, g.x, g.y, x[s], y[s], z[s], tm, h, m2[s]);
+#pragma unroll 1
+                for (int j = 7; j < n; j += 4) {
+                    const uint2 q = __ldg(++list);
+                    dyn_group(e.drec, q.x, q.y, x[s], y[s], z[s], tm, h, m2[s]);
+                }
+            } else {
+                dyn_brute_force(e.dynA, e.dynB, e.n_dyn, x[s], y[s], z[s], tm, h, m2[s]);
+            }
+            hit |= h ? (1u << s) : 0u;
+        }
+    }
+#else
     int cell = dyn_cell(e, x[0], y[0], z[0], t0);
     uint4 head = dyn_head(e, cell);
 #pragma unroll
@@ -341,6 +392,7 @@ __device__ __forceinline__ void eval_dynamic(const EnvDev& e, const Tables& t, c
         dyn_walk(e, cur_cell, hd, x[s], y[s], z[s], ti, h, m2[s]);
         hit |= h ? (1u << s) : 0u;
     }
+#endif
 }
 
 // One point at an arbitrary (fractional) time — the sample points of the S > 1 extension: brute force unless the
@@ -569,7 +621,7 @@ __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_para
         const uint32_t word = __ballot_sync(0xffffffffu, h);
         if (lane == c) out.cw[s] = word;
         ncoll += h ? 1 : 0;
-        if (has_dist && valid) a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[s])));  // HR:46
+        if (has_dist && valid) a_prox = __fadd_rn(a_prox, rcp_rn(__fadd_rn(1.0f, dn[s])));  // HR:46
         if constexpr (XF >= 1) {
             if (e.hazard != nullptr && valid) a_haz = __fadd_rn(a_haz, hazard_sample(e, cur.x[s], cur.y[s], (float)k));
         }
@@ -586,7 +638,7 @@ __device__ __forceinline__ void reduce_chromosome(const EnvDev& e, const tf_para
                     eval_point_full<SEM, VOX, XF>(e, t, fmaf(dx, tj, px), fmaf(dy, tj, py), fmaf(dz, tj, pz),
                                                      __fadd_rn((float)(k - 1), tj), sh, sdn);
                     ncoll += sh ? 1 : 0;
-                    if (has_dist) a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, sdn)));
+                    if (has_dist) a_prox = __fadd_rn(a_prox, rcp_rn(__fadd_rn(1.0f, sdn)));
                 }
             }
         }

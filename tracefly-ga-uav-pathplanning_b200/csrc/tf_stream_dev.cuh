@@ -110,7 +110,7 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
         const uint32_t word = __ballot_sync(0xffffffffu, h);
         if (lane == c) out.cw[s] = word;
         ncoll += h ? 1 : 0;
-        if (has_dist) a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[s])));  // HR:46
+        if (has_dist) a_prox = __fadd_rn(a_prox, rcp_rn(__fadd_rn(1.0f, dn[s])));  // HR:46
         if constexpr (XF >= 1) {
             if (e.hazard != nullptr) a_haz = __fadd_rn(a_haz, hazard_sample(e, cur.x[s], cur.y[s], (float)k));
         }
@@ -128,7 +128,7 @@ __device__ __forceinline__ void reduce_fullw(const EnvDev& e, const tf_params& p
                     eval_point_full<SEM, VOX, XF>(e, t, fmaf(dx, tj, px), fmaf(dy, tj, py), fmaf(dz, tj, pz),
                                                      __fadd_rn((float)(k - 1), tj), sh, sdn);
                     ncoll += sh ? 1 : 0;
-                    if (has_dist) a_prox = __fadd_rn(a_prox, __fdiv_rn(1.0f, __fadd_rn(1.0f, sdn)));
+                    if (has_dist) a_prox = __fadd_rn(a_prox, rcp_rn(__fadd_rn(1.0f, sdn)));
                 }
             }
         }
@@ -353,6 +353,9 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 #ifndef TF_PROBE_FIRST
 #define TF_PROBE_FIRST 1
 #endif
+#ifndef TF_BATCH_MATH   // A/B: 0 = one sqrt_rn / rcp_rn call per waypoint, 1 = batched per lane in the XF 1 variants, 2 = everywhere
+#define TF_BATCH_MATH 1
+#endif
 // Row staging of duo_kernel: the owning lane's two TMA bulk copies, or — kGather — per-lane 16-byte cp.async copies
 // (every lane fetches its own waypoints from whichever parent covers them; the plan comes from the owning lane by three
 // shuffles).  Bit-identical.  Measured (round 2, same box, default run): cfg3 0.3757 -> 0.3733 ms, cfg4 0.9529 -> 0.9175 ms:
@@ -553,15 +556,33 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
                     if (live && ok) stg_stream_hint(dst + k, c4, pol_stream);
                 }
             };
+            // kBatch (XF 1): the square roots / reciprocals of a lane's NL waypoints are taken together (sqrt_rn_n,
+            // rcp_rn_n: one straight-line block behind one rare-input branch instead of NL branches around NL calls);
+            // the sums still take their terms in waypoint order, so every add has the same operands
+            constexpr bool kBatch = TF_BATCH_MATH > 1 || (TF_BATCH_MATH == 1 && XF == 1);
+            float seg2[NL];
             auto segment = [&](int m) {   // segment (k - 1, k)
                 const int k = h + 16 * m, v = m & 1;
                 const bool ok = !RAGW || k < W;
+                if constexpr (kBatch) seg2[m] = 0.0f;
                 if (ok && (m > 0 || h > 0)) {  // k >= 1
                     const float4 q = row[k - 1];
                     const float dx = cur.x[m] - q.x, dy = cur.y[m] - q.y, dz = cur.z[m] - q.z;
-                    a_dist[v] = __fadd_rn(a_dist[v], sqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
+                    if constexpr (kBatch) seg2[m] = dist2(dx, dy, dz);
+                    else a_dist[v] = __fadd_rn(a_dist[v], sqrt_rn(dist2(dx, dy, dz)));  // HR:51-52
                     a_alt[v] = __fadd_rn(a_alt[v], fabsf(dz));                      // HR:44
                     if (RAGW ? k <= W - 2 : (m < NL - 1 || h < 15)) turns += (cur.x[m] != q.x || cur.y[m] != q.y) ? 1 : 0;  // k <= W-2, HR:38-40,43
+                }
+            };
+            auto segment_lengths = [&]() {
+                if constexpr (kBatch) {
+                    float len[NL];
+                    sqrt_rn_n<NL>(seg2, len);
+#pragma unroll
+                    for (int m = 0; m < NL; ++m) {
+                        const int k = h + 16 * m;
+                        if ((!RAGW || k < W) && (m > 0 || h > 0)) a_dist[m & 1] = __fadd_rn(a_dist[m & 1], len[m]);  // HR:51-52
+                    }
                 }
             };
             VoxRegs<NL> vr;
@@ -571,9 +592,11 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
                 voxel_prefetch<NL>(e, cur, vr, pol_keep);
 #pragma unroll
                 for (int m = 0; m < NL; ++m) segment(m);
+                segment_lengths();
             } else {
 #pragma unroll
                 for (int m = 0; m < NL; ++m) { fetch(m); segment(m); }
+                segment_lengths();
                 if constexpr (VOX) voxel_prefetch<NL>(e, cur, vr, pol_keep);
             }
             PointAcc<NL, SEM> acc;
@@ -605,16 +628,33 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
 #pragma unroll
                     for (int m = 0; m < NL; ++m) m2[m] = INFINITY;
                     eval_dynamic<NL>(e, tabs, cur.x, cur.y, cur.z, h, 16, hit, m2);
+                    if constexpr (kBatch) {
+                        float d[NL];
+                        sqrt_rn_n<NL>(m2, d);
 #pragma unroll
-                    for (int m = 0; m < NL; ++m) dn[m] = fminf(dn[m], sqrt_rn(m2[m]));
+                        for (int m = 0; m < NL; ++m) dn[m] = fminf(dn[m], d[m]);
+                    } else {
+#pragma unroll
+                        for (int m = 0; m < NL; ++m) dn[m] = fminf(dn[m], sqrt_rn(m2[m]));
+                    }
                 }
             }
             uint32_t cwords[NL];
             if (has_dist) {
+                float term[NL];
+                if constexpr (kBatch) {
+                    float den[NL];
+#pragma unroll
+                    for (int m = 0; m < NL; ++m) den[m] = __fadd_rn(1.0f, dn[m]);
+                    rcp_rn_n<NL>(den, term);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < NL; ++m) term[m] = rcp_rn(__fadd_rn(1.0f, dn[m]));
+                }
 #pragma unroll
                 for (int m = 0; m < NL; ++m) {
                     if (RAGW && h + 16 * m >= W) continue;
-                    a_prox[m & 1] = __fadd_rn(a_prox[m & 1], __fdiv_rn(1.0f, __fadd_rn(1.0f, dn[m])));  // HR:46
+                    a_prox[m & 1] = __fadd_rn(a_prox[m & 1], term[m]);  // HR:46
                 }
             }
 #pragma unroll
