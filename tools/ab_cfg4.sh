@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 VARS=${@:-$(ls gpurun_ab)}
 for v in $VARS; do
   lib=$PWD/gpurun_ab/$v/libtracefly_b200.so
+  [ "$v" = product ] && lib=$PWD/tracefly-ga-uav-pathplanning_b200/_build/libtracefly_b200.so
   [ -f "$lib" ] || continue
   for wl in ${WL:-cfg4}; do
     TRACEFLY_B200_LIB=$lib python bench.py --workload $wl --no-e2e --no-cpu --no-extras --steps 20 --warmup 5 > gpurun_out/ab_${v}_${wl}.json 2> gpurun_out/ab_${v}_${wl}.err

@@ -11,7 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # TF_BUILD_DIR / TF_NVCC_EXTRA: A/B builds of kernel variants (e.g. -DTF_DUO_XF1_CTAS=2) next to the product
-# library; tracefly_b200._lib loads such a variant when TRACEFLY_B200_LIB points at it.
+# library; tracefly_b200._lib loads such a variant when TRACEFLY_B200_LIB points at it.  TF_NO_LINEINFO=1 drops -lineinfo
+# (smaller A/B libraries).
 OUT_DIR = os.environ.get("TF_BUILD_DIR") or os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libtracefly_b200.so")
 SOURCES = ["tf_env.cu", "tf_fitness.cu", "tf_rank.cu", "tf_ga.cu", "tf_io.cu", "tf_tape.cu"]
@@ -66,7 +67,7 @@ def build(force=False, verbose=False):
     while pending or running:
         while pending and len(running) < MAX_JOBS:
             src, obj, defs = pending.pop(0)
-            cmd = [nvcc()] + NVCC_FLAGS + os.environ.get("TF_NVCC_EXTRA", "").split() + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+            cmd = [nvcc()] + [f for f in NVCC_FLAGS if f != "-lineinfo" or not os.environ.get("TF_NO_LINEINFO")] + os.environ.get("TF_NVCC_EXTRA", "").split() + defs + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
             running.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         src, obj, proc = running.pop(0)
         out, _ = proc.communicate()

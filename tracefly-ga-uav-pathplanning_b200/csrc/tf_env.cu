@@ -133,9 +133,13 @@ constexpr int kIdxThreads = 128;
 constexpr int kIdxMaxPerThread = 16;  // n_dyn <= 2048
 __global__ void __launch_bounds__(kIdxThreads)
 build_dyn_index_kernel(const float4* __restrict__ dynA, const float4* __restrict__ dynB, int n, int T, int band, int gx,
-                       int gy, int gz, float ox, float oy, float oz, float h, int cap, uint16_t* __restrict__ cand) {
+                       int gy, int gz, float ox, float oy, float oz, float h, int cap, uint2* __restrict__ heads,
+                       uint16_t* __restrict__ ext, unsigned int ext_slots, unsigned int* __restrict__ ext_used) {
+    // cap = words per list in ext (a multiple of 4); heads / ext: EnvDev::dcand / dext
     __shared__ float red[kIdxThreads];
     __shared__ int n_list;
+    __shared__ unsigned int slot_s;
+    __shared__ uint16_t lst[1024];
     const size_t ncell = (size_t)gx * gy * gz;
     const size_t cellid = blockIdx.x;
     const int tb = (int)(cellid / ncell);
@@ -175,18 +179,29 @@ build_dyn_index_kernel(const float4* __restrict__ dynA, const float4* __restrict
     for (int k = threadIdx.x; k < n; k += kIdxThreads, ++j) {
         if ((marked >> j) & 1u) {
             const int pos = atomicAdd(&n_list, 1);
-            if (pos < cap - 1) cand[cellid * cap + 1 + pos] = (uint16_t)(2 * k);   // word 0 of a list is its length
+            if (pos < cap) lst[pos] = (uint16_t)(2 * k);
         }
     }
     __syncthreads();
+    // (a list is never empty — the nearest sphere of every time slice is on it — and the walk relies on that: an
+    // empty one would be marked as overflowed)
+    const int nl = n_list;
+    const bool fits = nl >= 1 && nl <= cap;
+    if (fits && nl > 3) {   // a slot in ext; when ext is full the list counts as overflowed and the host retries
+        if (threadIdx.x == 0) slot_s = atomicAdd(ext_used, 1u);
+        __syncthreads();
+        if (slot_s < ext_slots)
+            for (int i = threadIdx.x; i < cap; i += kIdxThreads) ext[(size_t)slot_s * cap + i] = lst[i < nl ? i : 0];
+    }
     if (threadIdx.x == 0) {
-        // (a list is never empty — the nearest sphere of every time slice is on it — and the walk relies on that: an
-        // empty one would be marked as overflowed)
-        cand[cellid * cap] = (uint16_t)(n_list >= 1 && n_list <= cap - 1 ? n_list : 0xffff);
-        // the walk reads whole groups of entries ({1..3}, {4..7}, ...) without per-entry predicates: fill the last
-        // group with copies of the first entry (min / or are idempotent)
-        if (n_list > 0 && n_list <= cap - 1)
-            for (int pos = n_list; ((pos + 1) & 3) != 0; ++pos) cand[cellid * cap + 1 + pos] = cand[cellid * cap + 1];
+        uint2 hd = make_uint2(0xffffu, 0u);
+        if (fits && nl <= 3) {
+            const uint32_t e1 = lst[0], e2 = nl > 1 ? lst[1] : e1, e3 = nl > 2 ? lst[2] : e1;
+            hd = make_uint2((uint32_t)nl | (e1 << 16), e2 | (e3 << 16));
+        } else if (fits && slot_s < ext_slots) {
+            hd = make_uint2((uint32_t)nl | ((uint32_t)lst[0] << 16), slot_s);
+        }
+        heads[cellid] = hd;
     }
 }
 
@@ -427,7 +442,7 @@ extern "C" int tf_env_set_dynamic(tf_env* env, const tf_dyn_obstacle* dyn_host, 
     if (env->dyn_block) { cudaFree(env->dyn_block); env->dyn_block = nullptr; }
     env->d.n_dyn = env->d.n_dyn_smem = 0; env->d.dynA = env->d.dynB = nullptr;
     if (env->dindex_block) { cudaFree(env->dindex_block); env->dindex_block = nullptr; }
-    env->d.dcand = nullptr; env->d.drec = nullptr;
+    env->d.dcand = nullptr; env->d.dext = nullptr; env->d.drec = nullptr;
     if (n == 0) return TF_OK;
     std::vector<float> A((size_t)n * 4), B((size_t)n * 4);
     for (int i = 0; i < n; ++i) {
@@ -468,7 +483,7 @@ extern "C" int tf_env_build_dynamic_index(tf_env* env, int time_slices, int band
         magic = band_magic(band);
     }
     const int nbands = (time_slices + band - 1) / band;
-    cap = (cap + 1 + 7) & ~7;  // word 0 of a list is its length; lists are rows of 16-bit words read 16 bytes at a time
+    cap = (cap + 3) & ~3;  // words per list in ext: groups of four entries
     int g[3];
     for (int a = 0; a < 3; ++a) {
         if (!(box_hi[a] > box_lo[a])) return TF_ERR_SHAPE;
@@ -481,19 +496,39 @@ extern "C" int tf_env_build_dynamic_index(tf_env* env, int time_slices, int band
     int rc = ensure_device();
     if (rc != TF_OK) return rc;
     if (env->dindex_block) { cudaFree(env->dindex_block); env->dindex_block = nullptr; }
-    env->d.dcand = nullptr; env->d.drec = nullptr;
-    const size_t bytes_rec = (((size_t)env->d.n_dyn * 32 + 255) / 256) * 256, bytes_cand = nlist * (size_t)cap * 2;
-    TF_CUDA(cudaMalloc(&env->dindex_block, bytes_rec + bytes_cand));
-    float4* rec = (float4*)env->dindex_block;
-    uint16_t* cand = (uint16_t*)((char*)env->dindex_block + bytes_rec);
-    build_dyn_index_kernel<<<(unsigned)nlist, kIdxThreads, 0, (cudaStream_t)stream>>>(
-        env->d.dynA, env->d.dynB, env->d.n_dyn, time_slices, band, g[0], g[1], g[2], box_lo[0], box_lo[1], box_lo[2], cell,
-        cap, cand);
-    TF_LAUNCH_CHECK();
+    env->d.dcand = nullptr; env->d.dext = nullptr; env->d.drec = nullptr;
+    // [records | heads | ext | ext counter]; ext is sized for an eighth of the lists being longer than three entries and
+    // the build is repeated with the demanded size when that was not enough
+    auto r256 = [](size_t b) { return ((b + 255) / 256) * 256; };
+    const size_t bytes_rec = r256((size_t)env->d.n_dyn * 32), bytes_heads = r256(nlist * 8);
+    size_t ext_slots = nlist / 8 + 256;
+    float4* rec = nullptr;
+    uint2* heads = nullptr;
+    uint16_t* ext = nullptr;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const size_t bytes_ext = r256(ext_slots * (size_t)cap * 2);
+        TF_CUDA(cudaMalloc(&env->dindex_block, bytes_rec + bytes_heads + bytes_ext + 256));
+        rec = (float4*)env->dindex_block;
+        heads = (uint2*)((char*)env->dindex_block + bytes_rec);
+        ext = (uint16_t*)((char*)env->dindex_block + bytes_rec + bytes_heads);
+        unsigned int* used = (unsigned int*)((char*)env->dindex_block + bytes_rec + bytes_heads + bytes_ext);
+        TF_CUDA(cudaMemsetAsync(used, 0, 4, (cudaStream_t)stream));
+        build_dyn_index_kernel<<<(unsigned)nlist, kIdxThreads, 0, (cudaStream_t)stream>>>(
+            env->d.dynA, env->d.dynB, env->d.n_dyn, time_slices, band, g[0], g[1], g[2], box_lo[0], box_lo[1], box_lo[2], cell,
+            cap, heads, ext, (unsigned int)ext_slots, used);
+        TF_LAUNCH_CHECK();
+        unsigned int demanded = 0;
+        TF_CUDA(cudaMemcpyAsync(&demanded, used, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        TF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        if ((size_t)demanded <= ext_slots) break;
+        cudaFree(env->dindex_block);
+        env->dindex_block = nullptr;
+        ext_slots = demanded;
+    }
     dyn_records_kernel<<<(env->d.n_dyn + 255) / 256, 256, 0, (cudaStream_t)stream>>>(env->d.dynA, env->d.dynB, env->d.n_dyn, rec);
     TF_LAUNCH_CHECK();
     TF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    env->d.dcand = cand; env->d.drec = rec;
+    env->d.dcand = heads; env->d.dext = ext; env->d.drec = rec;
     env->d.dT = time_slices; env->d.dband = band; env->d.dgx = g[0]; env->d.dgy = g[1]; env->d.dgz = g[2]; env->d.dcap = cap;
     env->d.dox = box_lo[0]; env->d.doy = box_lo[1]; env->d.doz = box_lo[2]; env->d.dinv_h = 1.0f / cell;
     env->d.dband_magic = magic;
@@ -506,7 +541,7 @@ extern "C" int tf_env_dynamic_index_stats(const tf_env* env, int64_t* n_lists, i
     if (!env || !env->d.dcand) return TF_ERR_INVALID;
     const size_t n = (size_t)((env->d.dT + env->d.dband - 1) / env->d.dband) * env->d.dgx * env->d.dgy * env->d.dgz;
     std::vector<uint16_t> h(n);
-    TF_CUDA(cudaMemcpy2D(h.data(), 2, env->d.dcand, (size_t)env->d.dcap * 2, 2, n, cudaMemcpyDeviceToHost));
+    TF_CUDA(cudaMemcpy2D(h.data(), 2, env->d.dcand, 8, 2, n, cudaMemcpyDeviceToHost));   // word 0 of every 8-byte head
     int64_t over = 0;
     double sum = 0.0;
     int mx = 0;

@@ -215,9 +215,6 @@ __device__ __forceinline__ void eval_static(const EnvDev& e, const Tables& t, co
     else eval_static_chunk<SEM, NP>(e, t, 0, min(e.n, kTableCap), x, y, z, hit, best);
 }
 
-#ifndef TF_DYN_PHASED   // A/B: 1 = eval_dynamic walks its NP candidate lists in phases (below), 0 = list by list
-#define TF_DYN_PHASED 1
-#endif
 // Moving spheres (extension): HR rules at c(t) = c0 + v t.  Returns min d^2 per point.
 // With a candidate index (tf_env_build_dynamic_index) a point at an integer time slice inside the
 // index box only visits the spheres listed for its cell — a superset of "nearest" and of "colliding"
@@ -263,11 +260,9 @@ __device__ __forceinline__ void dyn_brute_force(const float4* __restrict__ dynA,
     m2 = m;
 }
 
-// The list of `cell` (head = its first 16 bytes, already loaded) against one point at integer time ti.
-// A list is a row of 16-bit words: word 0 = length (0xffff = overflow), words 1.. = 2 * sphere id (the offset of
-// its record in drec); the entries come in groups {1..3}, {4..7}, {8..11}, ... and the last group of a list is
-// filled up with copies of its first entry (min / or are idempotent), so a group is walked without per-entry
-// predicates and its loads go out together.  Lists of up to 7 spheres need no second list load.
+// Four listed spheres (two words of a list) against one point: a group is walked without per-entry predicates and its
+// loads go out together (the last group of a list is filled up with copies of the list's first entry; min / or are
+// idempotent).
 __device__ __forceinline__ void dyn_group(const float4* __restrict__ drec, uint32_t w0, uint32_t w1, float x, float y, float z,
                                           float tm, bool& h, float& m2) {
     dyn_test_rec(drec, (int)(w0 & 0xffffu), x, y, z, tm, h, m2);
@@ -275,44 +270,70 @@ __device__ __forceinline__ void dyn_group(const float4* __restrict__ drec, uint3
     dyn_test_rec(drec, (int)(w1 & 0xffffu), x, y, z, tm, h, m2);
     dyn_test_rec(drec, (int)(w1 >> 16), x, y, z, tm, h, m2);
 }
-__device__ __forceinline__ void dyn_walk(const EnvDev& e, int cell, const uint4 hd, float x, float y, float z, int ti, bool& h,
-                                         float& m2) {
-    const float tm = (float)ti;
-    const int n = (int)(hd.x & 0xffffu);
-    if (n != 0xffff) {
-        if (n > 0) {
-            dyn_test_rec(e.drec, (int)(hd.x >> 16), x, y, z, tm, h, m2);
-            dyn_test_rec(e.drec, (int)(hd.y & 0xffffu), x, y, z, tm, h, m2);
-            dyn_test_rec(e.drec, (int)(hd.y >> 16), x, y, z, tm, h, m2);
-        }
-        if (n > 3) dyn_group(e.drec, hd.z, hd.w, x, y, z, tm, h, m2);
-        if (n > 7) {
-            // (moving this rare tail and the brute-force fallback out of line shrinks the kernel by a third — it
-            // loses 8 % of its issue slots to instruction-cache misses — but the call's register saves cost more:
-            // cfg4 0.912 -> 0.989 ms)
-            const uint4* list = reinterpret_cast<const uint4*>(e.dcand + (size_t)(uint32_t)cell * (uint32_t)e.dcap) + 1;
-#pragma unroll 1
-            for (int j = 7; j < n; j += 8, ++list) {
-                const uint4 q = __ldg(list);
-                dyn_group(e.drec, q.x, q.y, x, y, z, tm, h, m2);
-                if (j + 4 < n) dyn_group(e.drec, q.z, q.w, x, y, z, tm, h, m2);
-            }
-        }
-    } else {
-        dyn_brute_force(e.dynA, e.dynB, e.n_dyn, x, y, z, tm, h, m2);
+// The indexed walk in three phases, so that the common case is ONE straight-line block:
+// (1) dyn_heads: the cells and the 8-byte heads of the NP lists (length + three words, EnvDev::dcand) — NP independent
+//     loads in flight;
+// (2) dyn_eval_heads: three tests per list, unconditionally: the entries of a list of up to three spheres (an indexed
+//     list holds at least the nearest sphere, and its head is filled up with copies of the first entry), the first entry
+//     three times for a longer list, sphere 0 three times for a point outside the index / an overflowed list (head
+//     (0xffff, 0); the loop over all spheres repeats it — min / or are idempotent);
+// (3) behind one branch, the lists longer than three entries (from dext, in groups of four) and the loop over all spheres.
+template <int NP>
+struct DynHeads {
+    uint2 hd[NP];
+};
+template <int NP>
+__device__ __forceinline__ void dyn_heads(const EnvDev& e, const float (&x)[NP], const float (&y)[NP], const float (&z)[NP],
+                                          int t0, int dt, DynHeads<NP>& d) {
+#pragma unroll
+    for (int s = 0; s < NP; ++s) {
+        const int cell = dyn_cell(e, x[s], y[s], z[s], t0 + dt * s);
+        d.hd[s] = make_uint2(0xffffu, 0u);
+        if (cell >= 0) d.hd[s] = __ldg(e.dcand + (uint32_t)cell);
     }
 }
-__device__ __forceinline__ uint4 dyn_head(const EnvDev& e, int cell) {
-    uint4 head = make_uint4(0xffffu, 0, 0, 0);
-    if (cell >= 0) head = __ldg(reinterpret_cast<const uint4*>(e.dcand + (size_t)(uint32_t)cell * (uint32_t)e.dcap));
-    return head;
+template <int NP>
+__device__ __forceinline__ void dyn_eval_heads(const EnvDev& e, const float (&x)[NP], const float (&y)[NP], const float (&z)[NP],
+                                               int t0, int dt, const DynHeads<NP>& d, uint32_t& hit, float (&m2)[NP]) {
+    float tm[NP];
+#pragma unroll
+    for (int s = 0; s < NP; ++s) tm[s] = (float)(t0 + dt * s);
+    bool rare = false;
+#pragma unroll
+    for (int s = 0; s < NP; ++s) {
+        const uint32_t n = d.hd[s].x & 0xffffu, e1 = d.hd[s].x >> 16;
+        const uint32_t w23 = n > 3u ? e1 * 0x10001u : d.hd[s].y;   // words 2..3 of a longer list are its slot in dext
+        bool h = false;
+        dyn_test_rec(e.drec, (int)e1, x[s], y[s], z[s], tm[s], h, m2[s]);
+        dyn_test_rec(e.drec, (int)(w23 & 0xffffu), x[s], y[s], z[s], tm[s], h, m2[s]);
+        dyn_test_rec(e.drec, (int)(w23 >> 16), x[s], y[s], z[s], tm[s], h, m2[s]);
+        hit |= h ? (1u << s) : 0u;
+        rare = rare || n > 3u;
+    }
+    if (rare) {
+#pragma unroll
+        for (int s = 0; s < NP; ++s) {
+            const int n = (int)(d.hd[s].x & 0xffffu);
+            if (n <= 3) continue;
+            bool h = false;
+            if (n != 0xffff) {
+                const uint2* list = reinterpret_cast<const uint2*>(e.dext + (size_t)d.hd[s].y * (uint32_t)e.dcap);
+#pragma unroll 1
+                for (int j = 0; j < n; j += 4) {
+                    const uint2 q = __ldg(list++);
+                    dyn_group(e.drec, q.x, q.y, x[s], y[s], z[s], tm[s], h, m2[s]);
+                }
+            } else {
+                dyn_brute_force(e.dynA, e.dynB, e.n_dyn, x[s], y[s], z[s], tm[s], h, m2[s]);
+            }
+            hit |= h ? (1u << s) : 0u;
+        }
+    }
 }
 
 // Moving spheres against NP points whose times are the INTEGERS t0, t0 + dt, ... (waypoint indices).
-// Without a candidate index: brute force over the records staged in shared memory.  With one: a list is
-// 16-byte aligned and starts with its length, so the first load of a waypoint brings the length and the first
-// seven entries.  The walk is a chain of two dependent loads (list head -> records); the head of slot s + 1 is
-// requested before slot s is walked.
+// Without a candidate index: brute force over the records staged in shared memory.  With one: the phased walk above
+// (a chain of two dependent loads per point, list head -> records; the NP heads go out together).
 template <int NP>
 __device__ __forceinline__ void eval_dynamic(const EnvDev& e, const Tables& t, const float (&x)[NP],
                                              const float (&y)[NP], const float (&z)[NP], int t0, int dt,
@@ -330,69 +351,9 @@ __device__ __forceinline__ void eval_dynamic(const EnvDev& e, const Tables& t, c
         }
         return;
     }
-#if TF_DYN_PHASED
-    // Three phases, so that the common case is ONE straight-line block: (1) the cells and the first 8 bytes of the NP
-    // lists (length + entries 1..3) — NP independent loads in flight; (2) entries 1..3 of every list, unconditionally
-    // (an indexed list holds at least the nearest sphere and its first group is padded; a point outside the index and an
-    // overflowed list read (0xffff, 0): three tests against sphere 0, which the loop over all spheres repeats — min / or
-    // are idempotent); (3) behind one branch, the lists longer than three entries and the loop over all spheres.
-    int cell[NP];
-    uint2 hd[NP];
-#pragma unroll
-    for (int s = 0; s < NP; ++s) {
-        cell[s] = dyn_cell(e, x[s], y[s], z[s], t0 + dt * s);
-        hd[s] = make_uint2(0xffffu, 0u);
-        if (cell[s] >= 0) hd[s] = __ldg(reinterpret_cast<const uint2*>(e.dcand + (size_t)(uint32_t)cell[s] * (uint32_t)e.dcap));
-    }
-    bool rare = false;
-#pragma unroll
-    for (int s = 0; s < NP; ++s) {
-        const float tm = (float)(t0 + dt * s);
-        bool h = false;
-        dyn_test_rec(e.drec, (int)(hd[s].x >> 16), x[s], y[s], z[s], tm, h, m2[s]);
-        dyn_test_rec(e.drec, (int)(hd[s].y & 0xffffu), x[s], y[s], z[s], tm, h, m2[s]);
-        dyn_test_rec(e.drec, (int)(hd[s].y >> 16), x[s], y[s], z[s], tm, h, m2[s]);
-        hit |= h ? (1u << s) : 0u;
-        rare = rare || (hd[s].x & 0xffffu) > 3u;
-    }
-    if (rare) {
-#pragma unroll
-        for (int s = 0; s < NP; ++s) {
-            const int n = (int)(hd[s].x & 0xffffu);
-            if (n <= 3) continue;
-            const float tm = (float)(t0 + dt * s);
-            bool h = false;
-            if (n != 0xffff) {
-                const uint2* list = reinterpret_cast<const uint2*>(e.dcand + (size_t)(uint32_t)cell[s] * (uint32_t)e.dcap) + 1;
-                const uint2 g = __ldg(list);
-                dyn_group(e.drec, g.x, g.y, x[s], y[s], z[s], tm, h, m2[s]);
-#pragma unroll 1
-                for (int j = 7; j < n; j += 4) {
-                    const uint2 q = __ldg(++list);
-                    dyn_group(e.drec, q.x, q.y, x[s], y[s], z[s], tm, h, m2[s]);
-                }
-            } else {
-                dyn_brute_force(e.dynA, e.dynB, e.n_dyn, x[s], y[s], z[s], tm, h, m2[s]);
-            }
-            hit |= h ? (1u << s) : 0u;
-        }
-    }
-#else
-    int cell = dyn_cell(e, x[0], y[0], z[0], t0);
-    uint4 head = dyn_head(e, cell);
-#pragma unroll
-    for (int s = 0; s < NP; ++s) {
-        const uint4 hd = head;
-        const int cur_cell = cell, ti = t0 + dt * s;
-        if (s + 1 < NP) {
-            cell = dyn_cell(e, x[s + 1], y[s + 1], z[s + 1], ti + dt);
-            head = dyn_head(e, cell);
-        }
-        bool h = false;
-        dyn_walk(e, cur_cell, hd, x[s], y[s], z[s], ti, h, m2[s]);
-        hit |= h ? (1u << s) : 0u;
-    }
-#endif
+    DynHeads<NP> d;
+    dyn_heads<NP>(e, x, y, z, t0, dt, d);
+    dyn_eval_heads<NP>(e, x, y, z, t0, dt, d, hit, m2);
 }
 
 // One point at an arbitrary (fractional) time — the sample points of the S > 1 extension: brute force unless the

@@ -40,16 +40,16 @@ __device__ __forceinline__ void rank_note(unsigned long long key, unsigned long 
     }
     __syncwarp();
 }
-// Called by every warp when it has run dry: the last one of the CTA merges the CTA's 8 x 2 keys into rank_part.
+// Called by every warp when it has run dry: the last one of the CTA merges the CTA's wpb x 2 keys into rank_part.
 __device__ __forceinline__ void rank_merge_cta(const unsigned long long* wbest_all, unsigned int* cta_done,
-                                               unsigned long long* __restrict__ rank_part, int lane) {
+                                               unsigned long long* __restrict__ rank_part, int lane, int wpb) {
     __threadfence_block();
     unsigned int nth = 0;
     if (lane == 0) nth = atomicAdd(cta_done, 1u);
-    if (__shfl_sync(0xffffffffu, nth, 0) == (unsigned int)kWarpsPerBlock - 1u) {
+    if (__shfl_sync(0xffffffffu, nth, 0) == (unsigned int)wpb - 1u) {
         __threadfence_block();
         unsigned long long a = ~0ull, b = ~0ull, first, second;
-        if (lane < kWarpsPerBlock) { a = wbest_all[2 * lane]; b = wbest_all[2 * lane + 1]; }
+        if (lane < wpb) { a = wbest_all[2 * lane]; b = wbest_all[2 * lane + 1]; }
         warp_two_smallest(a, b, first, second);
         if (lane == 0) {
             rank_part[2 * blockIdx.x] = first;
@@ -368,11 +368,17 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 #ifndef TF_GA_TAIL_TILES   // A/B: 0 = the plain fused generation runs on half-size tiles only; n = tiles of T with n
 #define TF_GA_TAIL_TILES 0 //      half-size tiles per resident warp at the end (re-measured with the 4-buffer ring: 0 wins)
 #endif
-template <int NW, int SEM, bool VOX, int XF, bool GA, bool RAGW>
 #ifndef TF_DUO_XF1_CTAS
 #define TF_DUO_XF1_CTAS 3
 #endif
-__global__ void __launch_bounds__(kBlockThreads, NW >= 8 ? 1 : NW >= 4 ? 2 : ((XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? TF_DUO_XF1_CTAS : 0)))
+#ifndef TF_DUO_XF1_WPB   // A/B: warps per CTA of the hazard / moving-sphere variants (W <= 64), e.g. 5 with TF_DUO_XF1_CTAS 4 = 20 warps at 96
+#define TF_DUO_XF1_WPB 8 // registers instead of 8 x 3 = 24 at 80 — measured: 5 x 4 CTAs (20 warps, 96 registers) 0.807 vs 0.801 ms, 6 x 3 0.857 ms
+#endif
+// CTA shape of duo_kernel: 8 warps; the XF 1 variants on rows of up to 64 waypoints take theirs from the knob above
+template <int NW, int XF>
+constexpr int duo_wpb() { return (XF == 1 && NW <= 2) ? TF_DUO_XF1_WPB : kWarpsPerBlock; }
+template <int NW, int SEM, bool VOX, int XF, bool GA, bool RAGW>
+__global__ void __launch_bounds__(duo_wpb<NW, XF>() * 32, NW >= 8 ? 1 : NW >= 4 ? 2 : ((XF == 0 && SEM == TF_SEM_NONE) ? 4 : (XF == 1 ? TF_DUO_XF1_CTAS : 0)))
 duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params prm,
            const __grid_constant__ tf_ga_params ga, const float4* __restrict__ pop,
            const float* __restrict__ fit, const int32_t* __restrict__ top_idx,
@@ -380,7 +386,7 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
            float4* __restrict__ next, float* __restrict__ out_fit, uint32_t* __restrict__ out_coll,
            int32_t* __restrict__ sel, int32_t* __restrict__ cpo, int n_big, int n_tickets, int* __restrict__ sched,
            int Wr, unsigned long long* __restrict__ rank_part, int32_t* __restrict__ next_top, int next_k) {
-    constexpr int NL = 2 * NW, kPairStages = kStages / 2;
+    constexpr int NL = 2 * NW, kPairStages = kStages / 2, kWpb = duo_wpb<NW, XF>();
     constexpr bool kGather = TF_ROW_GATHER > 0 || (TF_ROW_GATHER == 0 && XF == 1);
     const int W = RAGW ? Wr : 32 * NW;
     extern __shared__ __align__(128) unsigned char smem_stream[];
@@ -390,12 +396,12 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, h = lane & 15, half = lane >> 4;
     const size_t tables = (smem_bytes_for(e) + 127) & ~(size_t)127;
     float4* ring = reinterpret_cast<float4*>(smem + tables) + (size_t)warp * kStages * W;   // kPairStages x 2 rows
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tables + (size_t)kWarpsPerBlock * kStages * W * 16) + warp * kStages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tables + (size_t)kWpb * kStages * W * 16) + warp * kStages;
     const int ne = GA ? min(ga.n_elite, P) : 0;
     // fused ranking (GA, next_k = 1 or 2, dynamic schedule): the best keys this warp has produced so far, and the
     // CTA's count of warps that ran dry — behind the mbarriers
-    unsigned long long* wbest = reinterpret_cast<unsigned long long*>(bars - warp * kStages + kWarpsPerBlock * kStages) + warp * 2;
-    unsigned int* cta_done = reinterpret_cast<unsigned int*>(wbest - warp * 2 + kWarpsPerBlock * 2);
+    unsigned long long* wbest = reinterpret_cast<unsigned long long*>(bars - warp * kStages + kWpb * kStages) + warp * 2;
+    unsigned int* cta_done = reinterpret_cast<unsigned int*>(wbest - warp * 2 + kWpb * 2);
     const bool ranking = GA && next_k > 0;
 
     if (lane == 0) {
@@ -436,9 +442,9 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
         if (lane == 0) t = atomicAdd(sched, 1);
         return t;
     };
-    int ticket = dynamic ? __shfl_sync(0xffffffffu, draw(), 0) : (int)(blockIdx.x * kWarpsPerBlock) + warp;
+    int ticket = dynamic ? __shfl_sync(0xffffffffu, draw(), 0) : (int)(blockIdx.x * kWpb) + warp;
     while (ticket < n_tickets) {
-        const int ahead = dynamic ? draw() : ticket + (int)(gridDim.x * kWarpsPerBlock);
+        const int ahead = dynamic ? draw() : ticket + (int)(gridDim.x * kWpb);
         const int Tt = ticket < n_big ? T : (T >> 1), hT = Tt >> 1;
         const int slot0 = ticket < n_big ? ticket * T : n_big * T + (ticket - n_big) * Tt;
         const int cnt = min(Tt, P - slot0);
@@ -727,13 +733,13 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
         ticket = dynamic ? __shfl_sync(0xffffffffu, ahead, 0) : ahead;
     }
     if constexpr (GA) {
-        if (ranking) rank_merge_cta(wbest - warp * 2, cta_done, rank_part, lane);
+        if (ranking) rank_merge_cta(wbest - warp * 2, cta_done, rank_part, lane, kWpb);
     }
     // the last warp of the grid to run dry hands the counters back zeroed for the next launch and merges the CTAs'
     // ranking keys
     if (dynamic) {
         int last = 0;
-        if (lane == 0) last = atomicAdd(sched + 1, 1) == (int)(gridDim.x * kWarpsPerBlock) - 1;
+        if (lane == 0) last = atomicAdd(sched + 1, 1) == (int)(gridDim.x * kWpb) - 1;
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {
             if constexpr (GA) {
@@ -748,8 +754,10 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
 }
 
 template <int NW, int SEM, bool VOX, int XF, bool GA, bool RAGW>
-static int launch_duo(const StreamArgs& a, size_t smem, int T) {
+static int launch_duo(const StreamArgs& a, int T) {
     auto kern = duo_kernel<NW, SEM, VOX, XF, GA, RAGW>;
+    constexpr int kWpb = duo_wpb<NW, XF>();
+    const size_t smem = stream_smem_bytes(*a.e, a.W, kWpb);
     if (smem > 48 * 1024) TF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // resident CTAs per SM of this variant with this much shared memory.  One packed word (smem << 8 | occ): a
     // racing thread at worst repeats the query; the answer is the same on every B200 of a node.
@@ -757,10 +765,10 @@ static int launch_duo(const StreamArgs& a, size_t smem, int T) {
     const unsigned long long cached = __atomic_load_n(&occ_cache, __ATOMIC_RELAXED);
     int occ = (int)(cached & 0xffu);
     if ((cached >> 8) != (unsigned long long)smem || occ <= 0) {
-        TF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlockThreads, smem));
+        TF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWpb * 32, smem));
         __atomic_store_n(&occ_cache, ((unsigned long long)smem << 8) | (unsigned long long)(occ & 0xff), __ATOMIC_RELAXED);
     }
-    const int resident_warps = sm_count() * max(occ, 1) * kWarpsPerBlock;
+    const int resident_warps = sm_count() * max(occ, 1) * kWpb;
     // long runs (>= 4 tiles per resident warp): persistent grid, tickets from a global counter.  The plain fused
     // generation runs entirely on half-size tiles (16 children; measured at cfg3: tiles of 32 0.387 ms, 32 with
     // a tail of 2 / 4 / 8 half-size tiles per resident warp 0.385 / 0.378 / 0.377 ms, all 16 0.374 ms, all 8
@@ -769,7 +777,7 @@ static int launch_duo(const StreamArgs& a, size_t smem, int T) {
     // cfg4 1.17 -> 1.23 ms).  Short runs: static assignment.
     int n_big = (a.P + T - 1) / T, n_small = 0;
     int* sched = nullptr;
-    int grid = min((n_big + kWarpsPerBlock - 1) / kWarpsPerBlock, sm_count() * 8);
+    int grid = min((n_big + kWpb - 1) / kWpb, sm_count() * 8);
     if (T >= 8 && a.P / T >= 4 * resident_warps) {
         const int Ts = T >> 1;
         n_big = (GA && XF == 0 && TF_GA_TAIL_TILES == 0) ? 0 : (a.P - max(TF_GA_TAIL_TILES, 2) * resident_warps * Ts) / T;
@@ -784,7 +792,7 @@ static int launch_duo(const StreamArgs& a, size_t smem, int T) {
     // fused ranking of the children: only on the persistent grid (its last warp is the one that merges)
     const bool rank = GA && sched != nullptr && a.next_top != nullptr && (a.next_k == 1 || a.next_k == 2) &&
                       a.rank_part != nullptr && a.rank_part_bytes >= (int64_t)grid * 16 && a.P >= a.next_k;
-    kern<<<grid, kBlockThreads, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
+    kern<<<grid, kWpb * 32, smem, a.st>>>(*a.e, *a.prm, *a.ga, reinterpret_cast<const float4*>(a.pop), a.fit,
                                               a.top_idx, a.tape, a.seed, a.gen, a.P, T,
                                               reinterpret_cast<float4*>(a.next), a.out_fit, a.out_coll, a.sel, a.cpo,
                                               n_big, n_big + n_small, sched, a.W, a.rank_part, a.next_top, rank ? a.next_k : 0);
@@ -821,10 +829,10 @@ static int launch_stream(const StreamArgs& a) {
     }
     if constexpr (XF < 2) {
         if (a.W != 32 * NW) {
-            if constexpr (SEM == TF_SEM_NONE) return launch_duo<NW, SEM, VOX, XF, GA, true>(a, smem, T);
+            if constexpr (SEM == TF_SEM_NONE) return launch_duo<NW, SEM, VOX, XF, GA, true>(a, T);
             else return TF_ERR_UNSUPPORTED;  // stream_eligible() never sends these here
         }
-        return launch_duo<NW, SEM, VOX, XF, GA, false>(a, smem, T);
+        return launch_duo<NW, SEM, VOX, XF, GA, false>(a, T);
     } else {
         return TF_ERR_UNSUPPORTED;
     }
@@ -842,16 +850,15 @@ static int stream_flags(const StreamArgs& a) {
 // waypoints per lane; the ring is 12 / 24 KB per warp, so 2 CTAs / SM and 128 registers, or 1 and 255)
 template <int NW, bool GA>
 static int stream_long_rows(const StreamArgs& a) {
-    const size_t smem = stream_smem_bytes(*a.e, a.W);
     const int T = tile_size_for(a.P);
     const bool vox = a.e->bricks != nullptr;
     const bool xf1 = a.e->n_dyn > 0 || a.e->hazard != nullptr;
     if (a.W == 32 * NW) {
-        if (vox) return xf1 ? launch_duo<NW, TF_SEM_NONE, true, 1, GA, false>(a, smem, T) : launch_duo<NW, TF_SEM_NONE, true, 0, GA, false>(a, smem, T);
-        return xf1 ? launch_duo<NW, TF_SEM_NONE, false, 1, GA, false>(a, smem, T) : launch_duo<NW, TF_SEM_NONE, false, 0, GA, false>(a, smem, T);
+        if (vox) return xf1 ? launch_duo<NW, TF_SEM_NONE, true, 1, GA, false>(a, T) : launch_duo<NW, TF_SEM_NONE, true, 0, GA, false>(a, T);
+        return xf1 ? launch_duo<NW, TF_SEM_NONE, false, 1, GA, false>(a, T) : launch_duo<NW, TF_SEM_NONE, false, 0, GA, false>(a, T);
     }
-    if (vox) return xf1 ? launch_duo<NW, TF_SEM_NONE, true, 1, GA, true>(a, smem, T) : launch_duo<NW, TF_SEM_NONE, true, 0, GA, true>(a, smem, T);
-    return xf1 ? launch_duo<NW, TF_SEM_NONE, false, 1, GA, true>(a, smem, T) : launch_duo<NW, TF_SEM_NONE, false, 0, GA, true>(a, smem, T);
+    if (vox) return xf1 ? launch_duo<NW, TF_SEM_NONE, true, 1, GA, true>(a, T) : launch_duo<NW, TF_SEM_NONE, true, 0, GA, true>(a, T);
+    return xf1 ? launch_duo<NW, TF_SEM_NONE, false, 1, GA, true>(a, T) : launch_duo<NW, TF_SEM_NONE, false, 0, GA, true>(a, T);
 }
 template <int NW, bool GA>
 static int stream_sem(const StreamArgs& a) {

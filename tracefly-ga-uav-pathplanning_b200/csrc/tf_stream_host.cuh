@@ -14,11 +14,10 @@ namespace tf {
 #endif
 constexpr int kStages = TF_STAGES;
 
-__host__ __device__ inline size_t stream_smem_bytes(const EnvDev& e, int W) {
+__host__ __device__ inline size_t stream_smem_bytes(const EnvDev& e, int W, int wpb = kWarpsPerBlock) {
     size_t tables = (smem_bytes_for(e) + 127) & ~(size_t)127;
     // tables | row ring | mbarriers | fused ranking: two best keys per warp + the CTA's finished-warp counter
-    return tables + (size_t)kWarpsPerBlock * kStages * W * 16 + (size_t)kWarpsPerBlock * kStages * 8 +
-           (size_t)kWarpsPerBlock * 16 + 16;
+    return tables + (size_t)wpb * kStages * W * 16 + (size_t)wpb * kStages * 8 + (size_t)wpb * 16 + 16;
 }
 
 struct StreamArgs {
