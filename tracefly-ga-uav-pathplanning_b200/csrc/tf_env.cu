@@ -123,12 +123,14 @@ __global__ void pack_linear_kernel(const uint32_t* __restrict__ lin, uint32_t* _
     bricks[i] = out;
 }
 
-// Candidate index of the moving spheres.  One CTA per (time band, cell); a band covers `band`
-// consecutive integer times.  With m the cell centre, rho its half diagonal and dmin_t the distance
-// from m to the nearest sphere centre at time t, every sphere that can be NEAREST to some point of
-// the cell at time t has |m - c(t)| <= dmin_t + 2 rho, and every sphere that can COLLIDE with one
-// has |m - c(t)| <= R + rho.  A sphere is listed if either holds for any t of the band.  Both tests
-// carry a relative 1e-5 and an absolute 1e-3 margin for the float rounding of the cell assignment.
+// Candidate index of the moving spheres.  One CTA per (time band, cell); a band covers `band` consecutive integer
+// times.  For a sphere centre c(t), near(c) / far(c) = its distance to the nearest / farthest point of the cell (an
+// axis-aligned box).  Whatever point p of the cell is asked about at time t, its nearest sphere is at most
+// U_t = min_j far(c_j(t)) away, so a sphere can be NEAREST to some point of the cell only if near(c(t)) <= U_t, and it
+// can COLLIDE with one only if near(c(t)) <= R.  A sphere is listed if either holds for any t of the band.  The cell's
+// half extent carries a relative 1e-5 and an absolute 1e-3 margin for the float rounding of the cell assignment, and
+// so do both comparisons.  (Round 2 first bounded the cell by its circumscribed sphere — |m - c| <= dmin + 2 rho; the
+// box bounds list fewer spheres — cfg4: 1.68 instead of 1.78 per list — and a list of up to three needs no side table.)
 constexpr int kIdxThreads = 128;
 constexpr int kIdxMaxPerThread = 16;  // n_dyn <= 2048
 __global__ void __launch_bounds__(kIdxThreads)
@@ -146,31 +148,33 @@ build_dyn_index_kernel(const float4* __restrict__ dynA, const float4* __restrict
     const size_t c = cellid % ncell;
     const int ix = (int)(c % gx), iy = (int)((c / gx) % gy), iz = (int)(c / ((size_t)gx * gy));
     const float mx = ox + ((float)ix + 0.5f) * h, my = oy + ((float)iy + 0.5f) * h, mz = oz + ((float)iz + 0.5f) * h;
-    const float rho = 0.8660254f * h * 1.00001f + 1e-3f;
+    const float hh = 0.5f * h * 1.00001f + 1e-3f;   // half extent of the cell, with the margin
     uint32_t marked = 0;  // bit j: sphere threadIdx.x + j * kIdxThreads is a candidate
     if (threadIdx.x == 0) n_list = 0;
     for (int t = tb * band; t < min(T, (tb + 1) * band); ++t) {
         const float tm = (float)t;
-        float dmin = INFINITY;
+        float umin = INFINITY;   // smallest far distance of the cell (to its farthest corner) over the spheres
         for (int k = threadIdx.x; k < n; k += kIdxThreads) {
             const float4 o = dynA[k], v = dynB[k];
-            const float dx = mx - fmaf(v.x, tm, o.x), dy = my - fmaf(v.y, tm, o.y), dz = mz - fmaf(v.z, tm, o.z);
-            dmin = fminf(dmin, sqrtf(dx * dx + dy * dy + dz * dz));
+            const float fx = fabsf(mx - fmaf(v.x, tm, o.x)) + hh, fy = fabsf(my - fmaf(v.y, tm, o.y)) + hh,
+                        fz = fabsf(mz - fmaf(v.z, tm, o.z)) + hh;
+            umin = fminf(umin, sqrtf(fx * fx + fy * fy + fz * fz));
         }
         __syncthreads();
-        red[threadIdx.x] = dmin;
+        red[threadIdx.x] = umin;
         __syncthreads();
         for (int off = kIdxThreads / 2; off > 0; off >>= 1) {
             if (threadIdx.x < off) red[threadIdx.x] = fminf(red[threadIdx.x], red[threadIdx.x + off]);
             __syncthreads();
         }
-        const float near_lim = (red[0] + 2.0f * rho) * 1.00001f + 1e-3f;
+        const float near_lim = red[0] * 1.00001f + 1e-3f;
         int j = 0;
         for (int k = threadIdx.x; k < n; k += kIdxThreads, ++j) {
             const float4 o = dynA[k], v = dynB[k];
-            const float dx = mx - fmaf(v.x, tm, o.x), dy = my - fmaf(v.y, tm, o.y), dz = mz - fmaf(v.z, tm, o.z);
-            const float d = sqrtf(dx * dx + dy * dy + dz * dz);
-            const float coll_lim = (sqrtf(o.w) + rho) * 1.00001f + 1e-3f;
+            const float nx = fmaxf(fabsf(mx - fmaf(v.x, tm, o.x)) - hh, 0.0f), ny = fmaxf(fabsf(my - fmaf(v.y, tm, o.y)) - hh, 0.0f),
+                        nz = fmaxf(fabsf(mz - fmaf(v.z, tm, o.z)) - hh, 0.0f);
+            const float d = sqrtf(nx * nx + ny * ny + nz * nz);   // near distance of the cell
+            const float coll_lim = sqrtf(o.w) * 1.00001f + 1e-3f;
             if (d <= near_lim || d <= coll_lim) marked |= 1u << j;
         }
     }
