@@ -374,7 +374,7 @@ void tf_philox4x32_10(uint32_t key0, uint32_t key1, uint32_t c0, uint32_t c1, ui
 /* Self-test of the library's FP32 square root (rsqrt seed + fma Newton step, used for segment lengths and
  * obstacle distances; the FP32 model of HR:51-52 / PF:162 needs it correctly rounded): adds to
  * *mismatches_dev (u64, device, caller-zeroed) the number of bit patterns in [first_bits, first_bits + count)
- * whose result differs from sqrt.rn.f32.  count <= 2^32. */
+ * whose result differs from sqrt.rn.f32 (scalar and batched form).  count <= 2^32. */
 int tf_selftest_sqrt(uint32_t first_bits, uint64_t count, uint64_t* mismatches_dev, void* stream);
 /* Self-test of the library's FP32 reciprocal (MUFU.RCP seed + fma Newton step for 1 <= y < 2^126, div.rn elsewhere;
  * the proximity term 1 / (1 + d) of HR:46 in the FP32 model): adds to *mismatches_dev the number of bit patterns y in

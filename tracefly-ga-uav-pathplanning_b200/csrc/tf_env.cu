@@ -535,6 +535,7 @@ extern "C" int tf_env_build_dynamic_index(tf_env* env, int time_slices, int band
     env->d.dcand = heads; env->d.dext = ext; env->d.drec = rec;
     env->d.dT = time_slices; env->d.dband = band; env->d.dgx = g[0]; env->d.dgy = g[1]; env->d.dgz = g[2]; env->d.dcap = cap;
     env->d.dox = box_lo[0]; env->d.doy = box_lo[1]; env->d.doz = box_lo[2]; env->d.dinv_h = 1.0f / cell;
+    env->d.dnox = -box_lo[0] * env->d.dinv_h; env->d.dnoy = -box_lo[1] * env->d.dinv_h; env->d.dnoz = -box_lo[2] * env->d.dinv_h;
     env->d.dband_magic = magic;
     env->d.n_dyn_smem = 0;  // the kernels read the records through L1 / L2 now
     return TF_OK;
@@ -776,8 +777,13 @@ __global__ void selftest_sqrt_kernel(uint32_t lo, uint64_t n, unsigned long long
     unsigned long long mine = 0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const float x = __uint_as_float(lo + (uint32_t)i);
-        const uint32_t a = __float_as_uint(sqrt_rn(x)), b = __float_as_uint(__fsqrt_rn(x));
-        mine += (a != b && !(isnan(__uint_as_float(a)) && isnan(__uint_as_float(b)))) ? 1 : 0;
+        const float xs[2] = {x, 2.0f};
+        float rs[2];
+        sqrt_rn_n<2>(xs, rs);   // the batched form (it folds x == 0 in differently)
+        const uint32_t a = __float_as_uint(sqrt_rn(x)), a2 = __float_as_uint(rs[0]), b = __float_as_uint(__fsqrt_rn(x));
+        const bool nan_b = isnan(__uint_as_float(b));
+        mine += (a != b && !(isnan(__uint_as_float(a)) && nan_b)) ? 1 : 0;
+        mine += (a2 != b && !(isnan(__uint_as_float(a2)) && nan_b)) ? 1 : 0;
     }
     if (mine) atomicAdd(bad, mine);
 }

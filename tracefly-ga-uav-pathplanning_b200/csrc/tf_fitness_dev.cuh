@@ -236,10 +236,20 @@ __device__ __forceinline__ void dyn_test_rec(const float4* __restrict__ drec, in
     dyn_test(__ldg(drec + (uint32_t)rec), __ldg(drec + (uint32_t)rec + 1), x, y, z, tm, hit, m2);
 }
 
+#ifndef TF_DYN_CELL_FMA   // A/B: cell coordinates of the moving-sphere index by one fma per axis
+#define TF_DYN_CELL_FMA 1
+#endif
 // Cell of the candidate index for a point at integer time ti, or -1 (outside the index box / time range).
 __device__ __forceinline__ int dyn_cell(const EnvDev& e, float x, float y, float z, int ti) {
+#if TF_DYN_CELL_FMA
+    // one fma per axis.  It may put a point that sits within a few ulps of a cell wall into the neighbouring cell —
+    // which lists a superset of its nearest / colliding spheres too (the 1e-3 margin of tf_env_build_dynamic_index)
+    const int ix = __float2int_rd(fmaf(x, e.dinv_h, e.dnox)), iy = __float2int_rd(fmaf(y, e.dinv_h, e.dnoy)),
+              iz = __float2int_rd(fmaf(z, e.dinv_h, e.dnoz));
+#else
     const int ix = __float2int_rd((x - e.dox) * e.dinv_h), iy = __float2int_rd((y - e.doy) * e.dinv_h),
               iz = __float2int_rd((z - e.doz) * e.dinv_h);
+#endif
     const bool indexed = ti >= 0 && ti < e.dT && (unsigned)ix < (unsigned)e.dgx && (unsigned)iy < (unsigned)e.dgy &&
                          (unsigned)iz < (unsigned)e.dgz;
     if (!indexed) return -1;
@@ -397,7 +407,7 @@ template <int NW>
 struct VoxRegs {
     uint32_t word[NW], mask[NW];
 };
-template <int NW>
+template <int NW, bool HINT = true>
 __device__ __forceinline__ void voxel_prefetch(const EnvDev& e, const Lanes<NW>& p, VoxRegs<NW>& v, uint64_t keep_policy) {
 #pragma unroll
     for (int s = 0; s < NW; ++s) {
@@ -405,7 +415,9 @@ __device__ __forceinline__ void voxel_prefetch(const EnvDev& e, const Lanes<NW>&
         const bool inb = (unsigned)ix < (unsigned)e.nx && (unsigned)iy < (unsigned)e.ny && (unsigned)iz < (unsigned)e.nz;
         const uint32_t brick = (uint32_t)(ix >> 3) + (uint32_t)e.nbx * ((uint32_t)(iy >> 3) + (uint32_t)e.nby * (uint32_t)(iz >> 3));
         v.mask[s] = inb ? (1u << (((iy & 3) << 3) | (ix & 7))) : 0u;
-        v.word[s] = inb ? ldg_u32_hint(e.bricks + (size_t)brick * 16 + ((iz & 7) * 2 + ((iy & 7) >> 2)), keep_policy) : 0u;
+        const uint32_t* wp = e.bricks + (size_t)brick * 16 + ((iz & 7) * 2 + ((iy & 7) >> 2));
+        if constexpr (HINT) v.word[s] = inb ? ldg_u32_hint(wp, keep_policy) : 0u;
+        else v.word[s] = inb ? __ldg(wp) : 0u;
     }
 }
 

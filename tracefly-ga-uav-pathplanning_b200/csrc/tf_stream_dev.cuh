@@ -353,6 +353,9 @@ stream_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_param
 #ifndef TF_PROBE_FIRST
 #define TF_PROBE_FIRST 1
 #endif
+#ifndef TF_XF1_L2_HINTS // A/B: 0 = the hazard / moving-sphere variants of duo_kernel drop the L2 eviction hints (the two
+#define TF_XF1_L2_HINTS 1 //      createpolicy results do not stay in registers there: 18 instructions per pair to re-create them)
+#endif
 #ifndef TF_BATCH_MATH   // A/B: 0 = one sqrt_rn / rcp_rn call per waypoint, 1 = batched per lane in the XF 1 variants, 2 = everywhere
 #define TF_BATCH_MATH 1
 #endif
@@ -426,7 +429,8 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
     int head = 0;
     uint32_t phase = 0;
     const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
-    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+    constexpr bool kHints = !(XF == 1 && TF_XF1_L2_HINTS == 0);
+    const uint64_t pol_stream = kHints ? l2_policy_evict_first() : 0ull, pol_keep = kHints ? l2_policy_evict_last() : 0ull;
     auto next_stage = [](int st) { return st + 1 == kPairStages ? 0 : st + 1; };
     const bool has_dist = (SEM != TF_SEM_NONE) || (XF >= 1 && e.n_dyn > 0);
 
@@ -479,7 +483,10 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
                     const int k = h + 16 * m;
                     if (RAGW && k >= W) continue;
                     const float4* src = (k < cpc ? pa : pb) + 16 * m;
-                    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)m * 256u), "l"(src), "l"(pol_stream) : "memory");
+                    if constexpr (kHints)
+                        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)m * 256u), "l"(src), "l"(pol_stream) : "memory");
+                    else
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)m * 256u), "l"(src) : "memory");
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -559,7 +566,10 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
                 const float4 c4 = ok ? row[k] : make_float4(-1.0f, -1.0f, -1.0f, 0.0f);
                 cur.x[m] = c4.x; cur.y[m] = c4.y; cur.z[m] = c4.z;
                 if constexpr (GA) {
-                    if (live && ok) stg_stream_hint(dst + k, c4, pol_stream);
+                    if (live && ok) {
+                        if constexpr (kHints) stg_stream_hint(dst + k, c4, pol_stream);
+                        else stg_stream(dst + k, c4);
+                    }
                 }
             };
             // kBatch (XF 1): the square roots / reciprocals of a lane's NL waypoints are taken together (sqrt_rn_n,
@@ -595,7 +605,7 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
             if constexpr (kProbeFirst) {
 #pragma unroll
                 for (int m = 0; m < NL; ++m) fetch(m);
-                voxel_prefetch<NL>(e, cur, vr, pol_keep);
+                voxel_prefetch<NL, kHints>(e, cur, vr, pol_keep);
 #pragma unroll
                 for (int m = 0; m < NL; ++m) segment(m);
                 segment_lengths();
@@ -603,7 +613,7 @@ duo_kernel(const __grid_constant__ EnvDev e, const __grid_constant__ tf_params p
 #pragma unroll
                 for (int m = 0; m < NL; ++m) { fetch(m); segment(m); }
                 segment_lengths();
-                if constexpr (VOX) voxel_prefetch<NL>(e, cur, vr, pol_keep);
+                if constexpr (VOX) voxel_prefetch<NL, kHints>(e, cur, vr, pol_keep);
             }
             PointAcc<NL, SEM> acc;
             acc.reset();
