@@ -271,6 +271,8 @@ def time_generations(ctx, name, cfg, steps, warmup):
         island.step()
     if ctx.world > 1:
         island.migrate()  # untimed: NCCL communicator set-up and first-collective connect happen here
+        for _ in range(int(os.environ.get("TF_BENCH_WARM_EXCHANGES", 1))):
+            island.warm_up()  # ... and the first all-gather that runs BESIDE a generation kernel (throw-away, state unchanged)
     ctx.sync_all()
 
     sampler = ClockSampler(ctx.local_rank)
@@ -422,6 +424,7 @@ def island_gate(ctx):
     ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=3, mutation_rate=0.3)
     isl = ctx.IslandGA(torch.from_numpy(make(ctx.rank)[2]).cuda(), ga, seed=seed, elites=E, interval=interval, env=env,
                        params=L.default_params(dist_zero_guard=1), pipelined=True)
+    isl.warm_up()               # (a throw-away exchange leaves the island unchanged: the gate covers that too)
     for _ in range(gens):
         isl.step()
     isl.flush()

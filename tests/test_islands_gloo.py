@@ -75,8 +75,11 @@ def _worker(rank, world, port, outdir, pipelined):
     ops = OracleOps(oenv, 2, E, (world - 1) * E)
     isl = IslandGA(torch.from_numpy(pop), ga, seed=SEED, elites=E, interval=INTERVAL, ops=ops, pipelined=pipelined)
     assert isl.E == E and isl.world == world and isl.ga.stream_id == rank
-    for _ in range(GENS):
+    isl.warm_up()               # a throw-away pipelined exchange: must leave the island as it was
+    for g in range(GENS):
         isl.step()
+        if g == 1:
+            isl.warm_up()
     isl.flush()
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), pop=isl.pop.numpy(), fit=isl.fit.numpy(), mig=isl.migrations)
     dist.destroy_process_group()

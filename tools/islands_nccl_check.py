@@ -30,8 +30,11 @@ for pipelined in (True, False):
     ga = L.default_ga_params(selection=L.SEL_TOURNAMENT, tournament_k=3, mutation_rate=0.3)
     isl = IslandGA(torch.from_numpy(pop_h).cuda(), ga, seed=T.SEED, elites=T.E, interval=T.INTERVAL, env=env,
                    params=L.default_params(dist_zero_guard=1), pipelined=pipelined)
-    for _ in range(T.GENS):
+    isl.warm_up()               # throw-away pipelined exchange beside a generation kernel: state must not change
+    for g in range(T.GENS):
         isl.step()
+        if g == 1:
+            isl.warm_up()
     isl.flush()
     torch.cuda.synchronize()
     ref = T._simulate(world, pipelined)[rank]

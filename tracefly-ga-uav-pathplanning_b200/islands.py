@@ -199,6 +199,30 @@ class IslandGA:
         self._pending = False
         self.migrations += 1
 
+    def warm_up(self):
+        """One throw-away pass through the PIPELINED exchange — elite selection and packing, the all-gather on the side
+        stream beside a generation kernel that leaves SMs free for it, the victim selection — without changing the
+        island: the generation writes into the spare buffers (the next step overwrites them), the gathered rows are
+        never applied.  NCCL connects and sizes its channels for this message on the first collective that runs
+        beside a kernel, and that cost (several hundred microseconds at 8 ranks) otherwise lands in the first real
+        exchange.  Callers that time generations call it once before they start."""
+        if self.world <= 1 or self.E == 0 or self.interval <= 0 or not self.pipelined or self._pending:
+            return
+        if not self._top_valid:
+            self.ops.rank(self.fit, self.top)
+            self._top_valid = self.ntop is not None
+        self.ops.elites(self.fit, self.elite_idx)
+        self.ops.pack(self.pop, self.fit, self.elite_idx, self.send_rows, self.send_fit)
+        with self._side():
+            dist.all_gather_into_tensor(self.recv_rows.view(self.world * self.E, self.W, 4), self.send_rows, group=self.group)
+            dist.all_gather_into_tensor(self.recv_fit.view(self.world * self.E), self.send_fit, group=self.group)
+        self._pending = True
+        self.launch_generation()          # into nxt / nfit / ntop: not swapped in
+        self._pending = False
+        if hasattr(self.ops, "join_side_stream"):
+            self.ops.join_side_stream()
+        self.ops.worst(self.fit, self.worst_idx)
+
     def migrate(self):
         """Synchronous exchange on the current population (warm-up, non-pipelined mode)."""
         if self.world <= 1 or self.E == 0:
